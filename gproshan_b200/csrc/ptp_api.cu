@@ -1,0 +1,954 @@
+// Host side + kernels entry points of libptp_b200.so: the extern "C" ABI declared in include/ptp_b200.h.
+// Device algorithms live in ptp_device.cuh. Build: gproshan_b200/build.py (nvcc, sm_100a, -lineinfo).
+#include "../../include/ptp_b200.h"
+#include "ptp_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ptp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            char b_[512];                                                                                     \
+            snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorNoKernelImageForDevice ||                   \
+                                e_ == cudaErrorInsufficientDriver                                             \
+                            ? PTP_ERR_NO_DEVICE                                                               \
+                            : PTP_ERR_CUDA,                                                                   \
+                        b_);                                                                                  \
+        }                                                                                                     \
+    } while (0)
+
+constexpr int GRID_BLOCK = 512;   // threads per CTA, cooperative (whole-GPU) kernels
+constexpr int BATCH_BLOCK = 512;  // threads per CTA, one-solve-per-CTA kernels
+constexpr int FLAT_BLOCK = 256;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+template <class R> __global__ void k_pad_gt(const R *__restrict__ gt, R *__restrict__ gt4, u32 V)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // one thread per output scalar
+    if (i < (size_t)V * 4) {
+        const size_t v = i >> 2, c = i & 3;
+        gt4[i] = c < 3 ? gt[v * 3 + c] : R(0);
+    }
+}
+
+__device__ __forceinline__ u32 he_next(u32 he) { return 3 * (he / 3) + (he + 1) % 3; }
+__device__ __forceinline__ u32 he_prev(u32 he) { return 3 * (he / 3) + (he + 2) % 3; }
+
+// One-ring rows in for_star order (include/che.h:10): he = EVT[v]; he = OT[prev(he)] until back at EVT[v] or NIL.
+// Entry k = VT[next(he_k)]; an open fan appends VT[prev(he_last)] (che::link, src/che.cpp:102-112).
+// pass 0: rows with <= 8 entries are final, longer ones get the OVF marker and are counted;
+// pass 1: overflow rows allocate from the pool and store their entries.
+__global__ void k_ring_build(const u32 *__restrict__ VT, const u32 *__restrict__ OT, const u32 *__restrict__ EVT, u32 V,
+                             u32 H, u32 *__restrict__ ring8, u32 *__restrict__ pool, ull *counters, int pass)
+{
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    u32 *row = ring8 + (size_t)v * GL;
+    if (pass == 1 && row[0] != OVF) return;
+
+    const u32 he0 = EVT[v];
+    u32 buf[GL];
+    u32 cnt = 0, last = NIL;
+    bool open = false, bad = false;
+    u32 off = 0;
+    if (pass == 1) off = row[1];
+    if (he0 != NIL) {
+        if (he0 >= H) bad = true;
+        u32 he = he0;
+        while (!bad) {
+            const u32 n = VT[he_next(he)];
+            if (n >= V) { bad = true; break; }
+            if (cnt < GL) buf[cnt] = n;
+            if (pass == 1) pool[off + cnt] = n;
+            cnt++;
+            const u32 ph = he_prev(he);
+            const u32 o = OT[ph];
+            if (o == NIL) {
+                open = true;
+                last = VT[ph];
+                if (last >= V) bad = true;
+                break;
+            }
+            if (o >= H || cnt >= (1u << 23)) { bad = true; break; }
+            he = o;
+            if (he == he0) break;
+        }
+    }
+    if (bad) {
+        atomicAdd(counters + 1, 1ull);
+        for (u32 k = 0; k < GL; k++) row[k] = NIL;
+        return;
+    }
+    const u32 entries = cnt + (open ? 1u : 0u);
+    if (pass == 1) {
+        if (open) pool[off + cnt] = last;
+        return;
+    }
+    if (entries <= GL) {
+        if (open) buf[cnt] = last;
+        for (u32 k = 0; k < GL; k++) row[k] = k < entries ? buf[k] : NIL;
+        if (open) row[0] |= OPEN_BIT;
+    } else {
+        const u32 o2 = (u32)atomicAdd(counters, (ull)entries);
+        row[0] = OVF;
+        row[1] = o2;
+        row[2] = entries;
+        row[3] = open ? 1u : 0u;
+        for (u32 k = 4; k < GL; k++) row[k] = NIL;
+    }
+}
+
+struct TeamFlat { // plain grid-stride launch, no synchronisation
+    static constexpr bool kGrid = false;
+    __device__ __forceinline__ u32 cta() const { return blockIdx.x; }
+    __device__ __forceinline__ u32 nctas() const { return gridDim.x; }
+    __device__ __forceinline__ u32 sync(u32 = 0) { return 0; }
+    template <class T> static __device__ __forceinline__ T ld(const T *p) { return *p; }
+};
+
+template <class R>
+__global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 kcap, ull *bar)
+{
+    TeamGrid t{bar, 0};
+    bfs_run<R, TeamGrid>(t, m, w, sources, S, kcap);
+}
+
+template <class R> __global__ void k_inv_init(MeshView<R> m, Work<R> w)
+{
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < m.V) w.inv[v] = NIL;
+}
+template <class R> __global__ void k_inv_fill(MeshView<R> m, Work<R> w, u32 p)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < p) {
+        const u32 v = w.sorted[r];
+        if (v < m.V) atomicMin(&w.inv[v], r);
+    }
+}
+
+template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshView<R> m, Work<R> w)
+{
+    TeamFlat t;
+    layout_run<R, TeamFlat>(t, m, w, (u32)w.ctrl[C_REACHED]);
+}
+
+template <class R, bool CL>
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, ull *bar)
+{
+    TeamGrid t{bar, 0};
+    const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
+    const u32 d = ptp_run<R, TeamGrid, CL>(t, w, sources, S, nl, p);
+    scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
+}
+
+// one CTA per solve, CTAs pull source sets from a queue
+template <class R>
+__global__ void __launch_bounds__(BATCH_BLOCK)
+k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, ull *queue,
+          ull *totals)
+{
+    __shared__ u32 s_b;
+    TeamCta t;
+    const Work<R> w = works[blockIdx.x];
+    while (true) {
+        if (threadIdx.x == 0) s_b = (u32)atomicAdd(queue, 1ull);
+        __syncthreads();
+        const u32 b = s_b;
+        __syncthreads();
+        if (b >= B) break;
+        const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
+        const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
+        const u32 *src = sources + o0;
+        if (threadIdx.x == 0) w.ctrl[C_OVFALLOC] = 0;
+        bfs_run<R, TeamCta>(t, m, w, src, S, NIL);
+        const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
+        layout_run<R, TeamCta>(t, m, w, p);
+        const u32 d = ptp_run<R, TeamCta, false>(t, w, src, S, nl, p);
+        scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(totals + 0, w.ctrl[C_ITER]);
+            atomicAdd(totals + 1, w.ctrl[C_UPDATES]);
+            atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
+            atomicAdd(totals + 3, (ull)(nl ? nl - 1 : 0));
+            atomicAdd(totals + 4, (ull)p);
+        }
+    }
+}
+
+// arg-max of |x| with the smallest index on ties (cublasI?amax semantics, src/cuda/geodesics_ptp.cu:139-141);
+// appends the winner to the sample list. Single CTA: the array is read once, bandwidth-trivial next to a solve.
+template <class R> __global__ void __launch_bounds__(1024) k_argmax_append(const R *__restrict__ x, u32 V, u32 *samples, u32 n, R *maxval)
+{
+    __shared__ R s_v[32];
+    __shared__ u32 s_i[32];
+    R bv = R(-1);
+    u32 bi = NIL;
+    for (u32 i = threadIdx.x; i < V; i += blockDim.x) {
+        const R a = Ops<R>::abs(x[i]);
+        if (a > bv) { bv = a; bi = i; }   // strided scan keeps the smallest index per thread
+    }
+    for (u32 o = 16; o; o >>= 1) {
+        const R ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+        const u32 oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const u32 nw = blockDim.x >> 5;
+        bv = threadIdx.x < nw ? s_v[threadIdx.x] : R(-1);
+        bi = threadIdx.x < nw ? s_i[threadIdx.x] : NIL;
+        for (u32 o = 16; o; o >>= 1) {
+            const R ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const u32 oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { samples[n] = bi; *maxval = x[bi]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host structures
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+} // namespace
+
+struct ptp_mesh {
+    int device = 0;
+    int real_size = 0;
+    u64 V = 0, H = 0;
+    int num_sms = 0;
+    void *GT4 = nullptr;
+    u32 *ring8 = nullptr;
+    u32 *ovf = nullptr;
+    u64 ovf_total = 0;
+    u64 bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    // single-solve workspace (lazy)
+    u64 ws_scap = 0; // source capacity the workspace was sized for (0 = not allocated)
+    bool ws_cl = false, ws_top = false;
+    std::vector<void *> ws_allocs;
+    void *w_key = nullptr, *w_sorted = nullptr, *w_inv = nullptr, *w_limits = nullptr, *w_tile = nullptr, *w_posS = nullptr,
+         *w_ringS = nullptr, *w_ovfS = nullptr, *w_dist[2] = {nullptr, nullptr}, *w_cl[2] = {nullptr, nullptr},
+         *w_top = nullptr, *w_ctrl = nullptr, *w_bar = nullptr, *w_src = nullptr, *w_out = nullptr, *w_clout = nullptr,
+         *w_maxval = nullptr;
+    void *h_ctrl = nullptr; // pinned
+
+    // batched workspace (lazy)
+    u32 bt_slots = 0;
+    u64 bt_scap = 0;
+    std::vector<void *> bt_allocs;
+    void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr;
+    u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
+};
+
+namespace {
+
+int dev_alloc(ptp_mesh *m, void **p, size_t bytes, std::vector<void *> *track)
+{
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(p, bytes));
+    m->bytes += bytes;
+    if (track) track->push_back(*p);
+    return PTP_OK;
+}
+
+void free_list(ptp_mesh *m, std::vector<void *> &l)
+{
+    for (void *p : l) cudaFree(p);
+    l.clear();
+    (void)m;
+}
+
+template <class R> MeshView<R> mesh_view(const ptp_mesh *m)
+{
+    MeshView<R> v;
+    v.V = (u32)m->V;
+    v.GT4 = (const typename Ops<R>::vec4 *)m->GT4;
+    v.ring8 = m->ring8;
+    v.ovf = m->ovf;
+    return v;
+}
+
+template <class R> Work<R> work_view(const ptp_mesh *m)
+{
+    Work<R> w;
+    w.key = (ull *)m->w_key;
+    w.sorted = (u32 *)m->w_sorted;
+    w.inv = (u32 *)m->w_inv;
+    w.limits = (u32 *)m->w_limits;
+    w.tile_sum = (u32 *)m->w_tile;
+    w.posS = (typename Ops<R>::vec4 *)m->w_posS;
+    w.ringS = (u32 *)m->w_ringS;
+    w.ovfS = (u32 *)m->w_ovfS;
+    w.dist[0] = (R *)m->w_dist[0];
+    w.dist[1] = (R *)m->w_dist[1];
+    w.cl[0] = (u32 *)m->w_cl[0];
+    w.cl[1] = (u32 *)m->w_cl[1];
+    w.toplesets = nullptr;
+    w.ctrl = (ull *)m->w_ctrl;
+    return w;
+}
+
+// (re)allocate the single-solve workspace for up to `scap` sources
+template <class R> int ensure_workspace(ptp_mesh *m, u64 S, bool need_cl, bool need_top)
+{
+    if (m->ws_scap >= S && m->ws_scap != 0 && (!need_cl || m->ws_cl) && (!need_top || m->ws_top)) return PTP_OK;
+    const u64 scap = std::max<u64>(std::max<u64>(S, m->ws_scap), 1024);
+    const bool cl = need_cl || m->ws_cl, top = need_top || m->ws_top;
+    for (void *p : m->ws_allocs) cudaFree(p);
+    m->ws_allocs.clear();
+    m->ws_scap = 0;
+    const u64 V = m->V, N = V + scap;
+    int rc;
+#define WS(ptr, bytes)                                               \
+    if ((rc = dev_alloc(m, &(ptr), (bytes), &m->ws_allocs)) != PTP_OK) return rc;
+    WS(m->w_key, 8 * V)
+    WS(m->w_sorted, 4 * N)
+    WS(m->w_inv, 4 * V)
+    WS(m->w_limits, 4 * (V + 2))
+    WS(m->w_tile, 4 * 4096)
+    WS(m->w_posS, 4 * sizeof(R) * (N + 1))
+    WS(m->w_ringS, 4 * GL * N)
+    WS(m->w_ovfS, 4 * std::max<u64>(m->ovf_total, 4))
+    WS(m->w_dist[0], sizeof(R) * (N + 1))
+    WS(m->w_dist[1], sizeof(R) * (N + 1))
+    if (cl) {
+        WS(m->w_cl[0], 4 * (N + 1))
+        WS(m->w_cl[1], 4 * (N + 1))
+        WS(m->w_clout, 4 * V)
+    } else {
+        m->w_cl[0] = m->w_cl[1] = m->w_clout = nullptr;
+    }
+    if (top) { WS(m->w_top, 4 * V) } else m->w_top = nullptr;
+    WS(m->w_ctrl, 8 * C_COUNT)
+    WS(m->w_bar, 8 * 8)
+    WS(m->w_src, 4 * scap)
+    WS(m->w_out, sizeof(R) * V)
+    WS(m->w_maxval, 16)
+#undef WS
+    m->ws_scap = scap;
+    m->ws_cl = cl;
+    m->ws_top = top;
+    return PTP_OK;
+}
+
+int check_sources(const ptp_mesh *m, const u32 *sources, u64 n)
+{
+    if (!sources || n == 0) return fail(PTP_ERR_INVALID, "sources must be non-empty");
+    for (u64 i = 0; i < n; i++)
+        if (sources[i] >= m->V) return fail(PTP_ERR_INVALID, "source index out of range");
+    return PTP_OK;
+}
+
+template <class K> int coop_grid(K kernel, int block, const ptp_mesh *m, int *grid)
+{
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    if (per_sm < 1) return fail(PTP_ERR_CUDA, "cooperative kernel does not fit on an SM");
+    *grid = m->num_sms; // one CTA per SM: the fewest barrier participants that still cover the chip
+    return PTP_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// launch BFS (device toplesets). Leaves limits/sorted/inv/ctrl on the device.
+template <class R> int launch_bfs(ptp_mesh *m, u32 S, u32 kcap, bool want_top)
+{
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    w.toplesets = want_top ? (u32 *)m->w_top : nullptr;
+    int grid;
+    int rc = coop_grid(k_bfs_grid<R>, GRID_BLOCK, m, &grid);
+    if (rc) return rc;
+    const u32 *src = (const u32 *)m->w_src;
+    ull *bar = (ull *)m->w_bar;
+    void *args[] = {&mv, &w, &src, &S, &kcap, &bar};
+    CK(cudaMemsetAsync(m->w_bar, 0, 64, m->stream));
+    CK(cudaLaunchCooperativeKernel((void *)k_bfs_grid<R>, dim3(grid), dim3(GRID_BLOCK), args, 0, m->stream));
+    return PTP_OK;
+}
+
+template <class R> int launch_layout(ptp_mesh *m)
+{
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    const int grid = m->num_sms * 8;
+    k_layout<R><<<grid, FLAT_BLOCK, 0, m->stream>>>(mv, w);
+    CK(cudaGetLastError());
+    return PTP_OK;
+}
+
+template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
+{
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    int grid;
+    void *fn = cl ? (void *)k_solve_grid<R, true> : (void *)k_solve_grid<R, false>;
+    int rc = cl ? coop_grid(k_solve_grid<R, true>, GRID_BLOCK, m, &grid) : coop_grid(k_solve_grid<R, false>, GRID_BLOCK, m, &grid);
+    if (rc) return rc;
+    const u32 *src = (const u32 *)m->w_src;
+    R *out = (R *)m->w_out;
+    u32 *clo = (u32 *)m->w_clout;
+    ull *bar = (ull *)m->w_bar;
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &bar};
+    CK(cudaMemsetAsync(m->w_bar, 0, 64, m->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GRID_BLOCK), args, 0, m->stream));
+    return PTP_OK;
+}
+
+void fill_stats(const ptp_mesh *m, ptp_stats_t *st, u64 launches, double ms_top, double ms_solve, double ms_total)
+{
+    if (!st) return;
+    const ull *c = (const ull *)m->h_ctrl;
+    st->n_reached = c[C_REACHED];
+    st->n_levels = c[C_NLIMITS] ? c[C_NLIMITS] - 1 : 0;
+    st->iterations = c[C_ITER];
+    st->vertex_updates = c[C_UPDATES];
+    st->max_window = c[C_MAXWIN];
+    st->gpu_launches = launches;
+    st->ms_toplesets = ms_top;
+    st->ms_solve = ms_solve;
+    st->ms_total = ms_total;
+}
+
+template <class R>
+int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V, u64 H, int device, ptp_mesh_t **out)
+{
+    if (!out) return fail(PTP_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!GT || !VT || !OT || !EVT) return fail(PTP_ERR_INVALID, "null mesh table");
+    if (V == 0 || H == 0 || H % 3 != 0) return fail(PTP_ERR_INVALID, "need V > 0 and H = 3 * faces > 0");
+    if (V >= 0x7FFFFFF0ull || H >= 0xFFFFFFF0ull) return fail(PTP_ERR_INVALID, "mesh too large for 31-bit vertex ranks");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PTP_ERR_NO_DEVICE, "no such CUDA device");
+    CK(cudaSetDevice(device));
+
+    ptp_mesh *m = new (std::nothrow) ptp_mesh();
+    if (!m) return fail(PTP_ERR_INVALID, "out of host memory");
+    m->device = device;
+    m->real_size = (int)sizeof(R);
+    m->V = V;
+    m->H = H;
+    int rc = PTP_OK;
+    auto bail = [&](int code) {
+        ptp_mesh_destroy(m);
+        return code;
+    };
+#define CKM(call)                                     \
+    do {                                              \
+        rc = [&]() -> int { CK(call); return PTP_OK; }(); \
+        if (rc) return bail(rc);                      \
+    } while (0)
+
+    CKM(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CKM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto &e : m->ev) CKM(cudaEventCreate(&e));
+    CKM(cudaHostAlloc(&m->h_ctrl, 8 * C_COUNT, cudaHostAllocDefault));
+
+    void *d_gt = nullptr, *d_vt = nullptr, *d_ot = nullptr, *d_evt = nullptr, *d_cnt = nullptr;
+    CKM(cudaMalloc(&d_gt, sizeof(R) * 3 * V));
+    CKM(cudaMalloc(&d_vt, 4 * H));
+    CKM(cudaMalloc(&d_ot, 4 * H));
+    CKM(cudaMalloc(&d_evt, 4 * V));
+    CKM(cudaMalloc(&d_cnt, 16));
+    auto free_tmp = [&]() {
+        cudaFree(d_gt); cudaFree(d_vt); cudaFree(d_ot); cudaFree(d_evt); cudaFree(d_cnt);
+    };
+#define CKT(call)                                     \
+    do {                                              \
+        rc = [&]() -> int { CK(call); return PTP_OK; }(); \
+        if (rc) { free_tmp(); return bail(rc); }      \
+    } while (0)
+    CKT(cudaMemcpyAsync(d_gt, GT, sizeof(R) * 3 * V, cudaMemcpyHostToDevice, m->stream));
+    CKT(cudaMemcpyAsync(d_vt, VT, 4 * H, cudaMemcpyHostToDevice, m->stream));
+    CKT(cudaMemcpyAsync(d_ot, OT, 4 * H, cudaMemcpyHostToDevice, m->stream));
+    CKT(cudaMemcpyAsync(d_evt, EVT, 4 * V, cudaMemcpyHostToDevice, m->stream));
+    CKT(cudaMemsetAsync(d_cnt, 0, 16, m->stream));
+
+    if ((rc = dev_alloc(m, &m->GT4, sizeof(R) * 4 * V, nullptr))) { free_tmp(); return bail(rc); }
+    if ((rc = dev_alloc(m, (void **)&m->ring8, 4 * GL * V, nullptr))) { free_tmp(); return bail(rc); }
+
+    k_pad_gt<R><<<(unsigned)((V * 4 + 255) / 256), 256, 0, m->stream>>>((const R *)d_gt, (R *)m->GT4, (u32)V);
+    k_ring_build<<<(unsigned)((V + 127) / 128), 128, 0, m->stream>>>((const u32 *)d_vt, (const u32 *)d_ot, (const u32 *)d_evt,
+                                                                      (u32)V, (u32)H, m->ring8, nullptr, (ull *)d_cnt, 0);
+    CKT(cudaGetLastError());
+    ull cnt[2] = {0, 0};
+    CKT(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, m->stream));
+    CKT(cudaStreamSynchronize(m->stream));
+    if (cnt[1]) { free_tmp(); bail(0); return fail(PTP_ERR_MESH, "inconsistent CHE tables: a one-ring walk left the mesh or did not terminate"); }
+    m->ovf_total = cnt[0];
+    if (m->ovf_total >= 0xFFFFFFF0ull) { free_tmp(); bail(0); return fail(PTP_ERR_INVALID, "overflow pool too large"); }
+    if (m->ovf_total) {
+        if ((rc = dev_alloc(m, (void **)&m->ovf, 4 * m->ovf_total, nullptr))) { free_tmp(); return bail(rc); }
+        // pass 1 reuses the offsets stored in the rows by pass 0
+        k_ring_build<<<(unsigned)((V + 127) / 128), 128, 0, m->stream>>>((const u32 *)d_vt, (const u32 *)d_ot, (const u32 *)d_evt,
+                                                                          (u32)V, (u32)H, m->ring8, m->ovf, (ull *)d_cnt, 1);
+        CKT(cudaGetLastError());
+        CKT(cudaStreamSynchronize(m->stream));
+    }
+    free_tmp();
+#undef CKT
+#undef CKM
+    *out = m;
+    return PTP_OK;
+}
+
+template <class R> int upload_sources(ptp_mesh *m, const u32 *sources, u32 S)
+{
+    CK(cudaMemcpyAsync(m->w_src, sources, 4ull * S, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemsetAsync(m->w_ctrl, 0, 8 * C_COUNT, m->stream));
+    return PTP_OK;
+}
+
+int fetch_ctrl(ptp_mesh *m)
+{
+    CK(cudaMemcpyAsync(m->h_ctrl, m->w_ctrl, 8 * C_COUNT, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    return PTP_OK;
+}
+
+template <class R>
+int toplesets_impl(ptp_mesh *m, const u32 *sources, u32 S, u32 k, u32 *toplesets, u32 *sorted, u64 scap, u32 *limits, u64 lcap,
+                   u32 *n_limits, ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if ((rc = check_sources(m, sources, S))) return rc;
+    if ((rc = ensure_workspace<R>(m, S, false, toplesets != nullptr))) return rc;
+    if ((rc = upload_sources<R>(m, sources, S))) return rc;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    if ((rc = launch_bfs<R>(m, S, k, toplesets != nullptr))) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    if ((rc = fetch_ctrl(m))) return rc;
+    const ull *c = (const ull *)m->h_ctrl;
+    const u64 nl = c[C_NLIMITS], p = c[C_REACHED];
+    if (n_limits) *n_limits = (u32)nl;
+    if (limits) {
+        if (lcap < nl) return fail(PTP_ERR_CAPACITY, "limits buffer too small");
+        CK(cudaMemcpyAsync(limits, m->w_limits, 4 * nl, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (sorted) {
+        if (scap < p) return fail(PTP_ERR_CAPACITY, "sorted buffer too small (needs V + duplicate sources)");
+        CK(cudaMemcpyAsync(sorted, m->w_sorted, 4 * p, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (toplesets) CK(cudaMemcpyAsync(toplesets, m->w_top, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    const double ms = ev_ms(m->ev[0], m->ev[1]);
+    fill_stats(m, st, 1, ms, 0, ms);
+    return PTP_OK;
+}
+
+template <class R>
+int solve_impl(ptp_mesh *m, const u32 *sources, u32 S, const u32 *limits, u32 nl, const u32 *sorted, R *dist, u32 *clusters,
+               u32 cl_fill, ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if ((rc = check_sources(m, sources, S))) return rc;
+    if (!limits || !sorted || !dist || nl < 2) return fail(PTP_ERR_INVALID, "limits (>= 2 entries), sorted and dist are required");
+    if (nl > m->V + 2) return fail(PTP_ERR_INVALID, "limits longer than V + 2");
+    const u64 p = limits[nl - 1];
+    for (u32 i = 1; i < nl; i++)
+        if (limits[i] < limits[i - 1]) return fail(PTP_ERR_INVALID, "limits must be non-decreasing");
+    if (p > m->V + S) return fail(PTP_ERR_INVALID, "limits.back() exceeds V + n_sources");
+    if ((rc = ensure_workspace<R>(m, S, clusters != nullptr, false))) return rc;
+    if ((rc = upload_sources<R>(m, sources, S))) return rc;
+    CK(cudaMemcpyAsync(m->w_sorted, sorted, 4 * p, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->w_limits, limits, 4ull * nl, cudaMemcpyHostToDevice, m->stream));
+    ull hc[2] = {nl, p};
+    CK(cudaMemcpyAsync(m->w_ctrl, hc, 16, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    k_inv_init<R><<<(unsigned)((m->V + 255) / 256), 256, 0, m->stream>>>(mv, w);
+    k_inv_fill<R><<<(unsigned)((p + 255) / 256), 256, 0, m->stream>>>(mv, w, (u32)p);
+    CK(cudaGetLastError());
+    if ((rc = launch_layout<R>(m))) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    if ((rc = launch_solve<R>(m, S, clusters != nullptr, cl_fill))) return rc;
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
+    if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
+    if ((rc = fetch_ctrl(m))) return rc;
+    fill_stats(m, st, 4, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    return PTP_OK;
+}
+
+// device pipeline: sources already in w_src, ctrl zeroed. Records ev[0..2].
+template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
+{
+    int rc;
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    if ((rc = launch_bfs<R>(m, S, NIL, false))) return rc;
+    if ((rc = launch_layout<R>(m))) return rc;
+    CK(cudaEventRecord(m->ev[1], m->stream));
+    if ((rc = launch_solve<R>(m, S, cl, cl_fill))) return rc;
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    return PTP_OK;
+}
+
+template <class R>
+int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *clusters, u32 cl_fill, u32 *sorted_index, u64 scap,
+                   ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if ((rc = check_sources(m, sources, S))) return rc;
+    if (!dist) return fail(PTP_ERR_INVALID, "dist is null");
+    if ((rc = ensure_workspace<R>(m, S, clusters != nullptr, false))) return rc;
+    if ((rc = upload_sources<R>(m, sources, S))) return rc;
+    if ((rc = pipeline<R>(m, S, clusters != nullptr, cl_fill))) return rc;
+    CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
+    if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
+    if (sorted_index) {
+        // p is only known on the device; copy what the caller can hold and validate afterwards
+        const u64 n = std::min<u64>(scap, m->V + S);
+        CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if ((rc = fetch_ctrl(m))) return rc;
+    fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    if (sorted_index && scap < ((const ull *)m->h_ctrl)[C_REACHED])
+        return fail(PTP_ERR_CAPACITY, "sorted_index buffer too small (needs V + duplicate sources)");
+    return PTP_OK;
+}
+
+template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off, u64 rows_elems)
+{
+    int rc;
+    if (m->bt_slots == 0 || m->bt_scap < max_s) {
+        free_list(m, m->bt_allocs);
+        m->bt_slots = 0;
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R>, BATCH_BLOCK, 0));
+        if (per_sm < 1) return fail(PTP_ERR_CUDA, "batched kernel does not fit on an SM");
+        const u32 slots = (u32)(m->num_sms * per_sm);
+        const u64 V = m->V, scap = std::max<u64>(max_s, 16), N = V + scap;
+        std::vector<Work<R>> hw(slots);
+        auto &tr = m->bt_allocs;
+        char *b_key, *b_sorted, *b_inv, *b_limits, *b_tile, *b_pos, *b_ring, *b_ovf, *b_d0, *b_d1, *b_ctrl;
+        const u64 ovfn = std::max<u64>(m->ovf_total, 4);
+#define BT(ptr, per)                                                                     \
+    if ((rc = dev_alloc(m, (void **)&(ptr), (u64)(per) * slots, &tr)) != PTP_OK) return rc;
+        BT(b_key, 8 * V)
+        BT(b_sorted, 4 * N)
+        BT(b_inv, 4 * V)
+        BT(b_limits, 4 * (V + 2))
+        BT(b_tile, 64)
+        BT(b_pos, 4 * sizeof(R) * (N + 1))
+        BT(b_ring, 4 * GL * N)
+        BT(b_ovf, 4 * ovfn)
+        BT(b_d0, sizeof(R) * (N + 1))
+        BT(b_d1, sizeof(R) * (N + 1))
+        BT(b_ctrl, 8 * C_COUNT)
+#undef BT
+        for (u32 s = 0; s < slots; s++) {
+            Work<R> &w = hw[s];
+            w.key = (ull *)(b_key + (u64)s * 8 * V);
+            w.sorted = (u32 *)(b_sorted + (u64)s * 4 * N);
+            w.inv = (u32 *)(b_inv + (u64)s * 4 * V);
+            w.limits = (u32 *)(b_limits + (u64)s * 4 * (V + 2));
+            w.tile_sum = (u32 *)(b_tile + (u64)s * 64);
+            w.posS = (typename Ops<R>::vec4 *)(b_pos + (u64)s * 4 * sizeof(R) * (N + 1));
+            w.ringS = (u32 *)(b_ring + (u64)s * 4 * GL * N);
+            w.ovfS = (u32 *)(b_ovf + (u64)s * 4 * ovfn);
+            w.dist[0] = (R *)(b_d0 + (u64)s * sizeof(R) * (N + 1));
+            w.dist[1] = (R *)(b_d1 + (u64)s * sizeof(R) * (N + 1));
+            w.cl[0] = w.cl[1] = nullptr;
+            w.toplesets = nullptr;
+            w.ctrl = (ull *)(b_ctrl + (u64)s * 8 * C_COUNT);
+        }
+        if ((rc = dev_alloc(m, &m->bt_works, sizeof(Work<R>) * slots, &tr))) return rc;
+        if ((rc = dev_alloc(m, &m->bt_queue, 64, &tr))) return rc;
+        CK(cudaMemcpy(m->bt_works, hw.data(), sizeof(Work<R>) * slots, cudaMemcpyHostToDevice));
+        m->bt_slots = slots;
+        m->bt_scap = scap;
+        m->bt_src = m->bt_off = m->bt_rows = nullptr;
+        m->bt_src_cap = m->bt_off_cap = m->bt_rows_cap = 0;
+    }
+    if (m->bt_src_cap < n_src) {
+        if ((rc = dev_alloc(m, &m->bt_src, 4 * n_src, &m->bt_allocs))) return rc;
+        m->bt_src_cap = n_src;
+    }
+    if (m->bt_off_cap < n_off) {
+        if ((rc = dev_alloc(m, &m->bt_off, 8 * n_off, &m->bt_allocs))) return rc;
+        m->bt_off_cap = n_off;
+    }
+    if (m->bt_rows_cap < rows_elems) {
+        if ((rc = dev_alloc(m, &m->bt_rows, sizeof(R) * rows_elems, &m->bt_allocs))) return rc;
+        m->bt_rows_cap = rows_elems;
+    }
+    return PTP_OK;
+}
+
+template <class R>
+int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64 n_src, R *rows, int on_device, void *stream_,
+                 ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if (B == 0) return fail(PTP_ERR_INVALID, "empty batch");
+    if (!rows) return fail(PTP_ERR_INVALID, "rows is null");
+    if (!offsets && n_src != B) return fail(PTP_ERR_INVALID, "without offsets n_sources must equal n_batch");
+    if ((rc = check_sources(m, sources, n_src))) return rc;
+    u64 max_s = 1;
+    if (offsets) {
+        if (offsets[0] != 0 || offsets[B] != n_src) return fail(PTP_ERR_INVALID, "offsets must start at 0 and end at n_sources");
+        for (u32 b = 0; b < B; b++) {
+            if (offsets[b + 1] <= offsets[b]) return fail(PTP_ERR_INVALID, "every source set must be non-empty");
+            max_s = std::max<u64>(max_s, offsets[b + 1] - offsets[b]);
+        }
+    }
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : m->stream;
+    // host rows: stage through a device buffer of at most ~8 GiB, chunk by chunk
+    u64 chunk = B;
+    if (!on_device) {
+        const u64 budget = 8ull << 30;
+        chunk = std::max<u64>(1, std::min<u64>(B, budget / (sizeof(R) * m->V)));
+    }
+    if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V))) return rc;
+    CK(cudaMemcpyAsync(m->bt_src, sources, 4 * n_src, cudaMemcpyHostToDevice, stream));
+    if (offsets) CK(cudaMemcpyAsync(m->bt_off, offsets, 8 * (u64)(B + 1), cudaMemcpyHostToDevice, stream));
+    ull *queue = (ull *)m->bt_queue;
+    CK(cudaMemsetAsync(queue, 0, 64, stream));
+    CK(cudaEventRecord(m->ev[0], stream));
+    MeshView<R> mv = mesh_view<R>(m);
+    u64 launches = 0;
+    for (u64 first = 0; first < B; first += chunk) {
+        const u32 nb = (u32)std::min<u64>(chunk, B - first);
+        R *dst = on_device ? rows + first * m->V : (R *)m->bt_rows;
+        CK(cudaMemsetAsync(queue, 0, 8, stream));
+        const u32 grid = std::min<u32>(m->bt_slots, nb);
+        k_batched<R><<<grid, BATCH_BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
+                                                        offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst, queue,
+                                                        queue + 1);
+        CK(cudaGetLastError());
+        launches++;
+        if (!on_device)
+            CK(cudaMemcpyAsync(rows + first * m->V, m->bt_rows, sizeof(R) * (u64)nb * m->V, cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaEventRecord(m->ev[1], stream));
+    ull tot[8];
+    CK(cudaMemcpyAsync(tot, queue, 64, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (st) {
+        st->iterations = tot[1];
+        st->vertex_updates = tot[2];
+        st->max_window = tot[3];
+        st->n_levels = tot[4];
+        st->n_reached = tot[5];
+        st->gpu_launches = launches;
+        st->ms_toplesets = 0;
+        st->ms_solve = st->ms_total = ev_ms(m->ev[0], m->ev[1]);
+    }
+    return PTP_OK;
+}
+
+template <class R>
+int fps_impl(ptp_mesh *m, u32 *samples, u32 n_initial, u32 n_total, R radio, u32 *n_out, R *max_dist, ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if (!samples || n_initial == 0) return fail(PTP_ERR_INVALID, "need at least one initial sample");
+    if ((rc = check_sources(m, samples, n_initial))) return rc;
+    // src/cuda/geodesics_ptp.cu:125: n >= n_vertices is clamped to n_vertices / 2
+    u64 want = n_total;
+    if (want >= m->V) want = m->V >> 1;
+    u32 n = n_initial;
+    R maxd = (R)INFINITY;
+    if ((rc = ensure_workspace<R>(m, std::max<u64>(want, n_initial), false, false))) return rc;
+    CK(cudaMemcpyAsync(m->w_src, samples, 4ull * n, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaEventRecord(m->ev[3], m->stream));
+    u64 launches = 0, iters = 0, updates = 0;
+    // the reference loops `n -= samples.size(); while(n-- && max_dist > radio)` (:127-148)
+    while (n < want && maxd > radio) {
+        CK(cudaMemsetAsync(m->w_ctrl, 0, 8 * C_COUNT, m->stream));
+        if ((rc = pipeline<R>(m, n, false, 0))) return rc;
+        k_argmax_append<R><<<1, 1024, 0, m->stream>>>((const R *)m->w_out, (u32)m->V, (u32 *)m->w_src, n, (R *)m->w_maxval);
+        CK(cudaGetLastError());
+        launches += 4;
+        n++;
+        const bool last = n >= want;
+        if (radio > 0 || last) {
+            // the reference reads the maximum back only when it needs it (:143-144)
+            CK(cudaMemcpyAsync(&maxd, m->w_maxval, sizeof(R), cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+        }
+        (void)iters; (void)updates;
+    }
+    CK(cudaEventRecord(m->ev[2], m->stream));
+    CK(cudaMemcpyAsync(samples, m->w_src, 4ull * n, cudaMemcpyDeviceToHost, m->stream));
+    if ((rc = fetch_ctrl(m))) return rc;
+    if (n_out) *n_out = n;
+    if (max_dist) *max_dist = maxd;
+    fill_stats(m, st, launches, 0, 0, ev_ms(m->ev[3], m->ev[2]));
+    if (st) st->ms_solve = st->ms_total;
+    return PTP_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+
+extern "C" {
+
+const char *ptp_last_error(void) { return g_err.c_str(); }
+
+const char *ptp_version(void) { return "ptp_b200 0.1 (sm_100a)"; }
+
+int ptp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *ptp_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        g_err = "cudaHostAlloc failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void ptp_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int ptp_mesh_create_f32(const float *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT, uint64_t V, uint64_t H,
+                        int device, ptp_mesh_t **out)
+{
+    return mesh_create<float>(GT, VT, OT, EVT, V, H, device, out);
+}
+int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT, uint64_t V, uint64_t H,
+                        int device, ptp_mesh_t **out)
+{
+    return mesh_create<double>(GT, VT, OT, EVT, V, H, device, out);
+}
+
+void ptp_mesh_destroy(ptp_mesh_t *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void *p : m->ws_allocs) cudaFree(p);
+    for (void *p : m->bt_allocs) cudaFree(p);
+    cudaFree(m->GT4);
+    cudaFree(m->ring8);
+    cudaFree(m->ovf);
+    if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
+    for (auto &e : m->ev)
+        if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+uint64_t ptp_mesh_n_vertices(const ptp_mesh_t *m) { return m ? m->V : 0; }
+uint64_t ptp_mesh_n_half_edges(const ptp_mesh_t *m) { return m ? m->H : 0; }
+int ptp_mesh_real_size(const ptp_mesh_t *m) { return m ? m->real_size : 0; }
+int ptp_mesh_device(const ptp_mesh_t *m) { return m ? m->device : -1; }
+uint64_t ptp_mesh_device_bytes(const ptp_mesh_t *m) { return m ? m->bytes : 0; }
+
+#define NEED(m, rs)                                                                     \
+    if (!(m)) return fail(PTP_ERR_INVALID, "mesh is null");                             \
+    if ((m)->real_size != (rs)) return fail(PTP_ERR_INVALID, "mesh precision does not match this entry point");
+
+int ptp_toplesets(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, uint32_t k, uint32_t *toplesets, uint32_t *sorted,
+                  uint64_t scap, uint32_t *limits, uint64_t lcap, uint32_t *n_limits, ptp_stats_t *st)
+{
+    if (!m) return fail(PTP_ERR_INVALID, "mesh is null");
+    return m->real_size == 4 ? toplesets_impl<float>(m, sources, S, k, toplesets, sorted, scap, limits, lcap, n_limits, st)
+                             : toplesets_impl<double>(m, sources, S, k, toplesets, sorted, scap, limits, lcap, n_limits, st);
+}
+
+int ptp_solve_f32(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, const uint32_t *limits, uint32_t nl, const uint32_t *sorted,
+                  float *dist, uint32_t *clusters, uint32_t fill, ptp_stats_t *st)
+{
+    NEED(m, 4) return solve_impl<float>(m, sources, S, limits, nl, sorted, dist, clusters, fill, st);
+}
+int ptp_solve_f64(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, const uint32_t *limits, uint32_t nl, const uint32_t *sorted,
+                  double *dist, uint32_t *clusters, uint32_t fill, ptp_stats_t *st)
+{
+    NEED(m, 8) return solve_impl<double>(m, sources, S, limits, nl, sorted, dist, clusters, fill, st);
+}
+
+int ptp_geodesics_f32(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, float *dist, uint32_t *clusters, uint32_t fill,
+                      uint32_t *sorted_index, uint64_t scap, ptp_stats_t *st)
+{
+    NEED(m, 4) return geodesics_impl<float>(m, sources, S, dist, clusters, fill, sorted_index, scap, st);
+}
+int ptp_geodesics_f64(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, double *dist, uint32_t *clusters, uint32_t fill,
+                      uint32_t *sorted_index, uint64_t scap, ptp_stats_t *st)
+{
+    NEED(m, 8) return geodesics_impl<double>(m, sources, S, dist, clusters, fill, sorted_index, scap, st);
+}
+
+int ptp_solve_batched_f32(ptp_mesh_t *m, const uint32_t *sources, const uint64_t *offsets, uint32_t B, uint64_t n_src, float *rows,
+                          int on_device, void *stream, ptp_stats_t *st)
+{
+    NEED(m, 4) return batched_impl<float>(m, sources, offsets, B, n_src, rows, on_device, stream, st);
+}
+int ptp_solve_batched_f64(ptp_mesh_t *m, const uint32_t *sources, const uint64_t *offsets, uint32_t B, uint64_t n_src, double *rows,
+                          int on_device, void *stream, ptp_stats_t *st)
+{
+    NEED(m, 8) return batched_impl<double>(m, sources, offsets, B, n_src, rows, on_device, stream, st);
+}
+
+int ptp_farthest_point_sampling_f32(ptp_mesh_t *m, uint32_t *samples, uint32_t n_initial, uint32_t n_total, float radio,
+                                    uint32_t *n_out, float *max_dist, ptp_stats_t *st)
+{
+    NEED(m, 4) return fps_impl<float>(m, samples, n_initial, n_total, radio, n_out, max_dist, st);
+}
+int ptp_farthest_point_sampling_f64(ptp_mesh_t *m, uint32_t *samples, uint32_t n_initial, uint32_t n_total, double radio,
+                                    uint32_t *n_out, double *max_dist, ptp_stats_t *st)
+{
+    NEED(m, 8) return fps_impl<double>(m, samples, n_initial, n_total, radio, n_out, max_dist, st);
+}
+
+} // extern "C"

@@ -1,0 +1,144 @@
+/* ptp_b200 — C ABI of the B200-native Parallel Toplesets Propagation (PTP) geodesic solver.
+ *
+ * Drop-in boundary for the PTP_GPU path of larc/gproshan. Plain pointers and sizes only; every
+ * entry point returns PTP_OK (0) or a negative error code, with ptp_last_error() giving the text.
+ * `file:line` citations are relative to the reference repository (larc/gproshan); each entry point
+ * names the reference interface it replaces. INTEGRATION.md shows the gproshan-side binding.
+ *
+ * Conventions (reference include/include.h:12-27, include/che.h:41-47):
+ *   index_t = uint32_t, NIL = 0xFFFFFFFF, real_t = float (f32 entry points) or double (f64).
+ *   Mesh = compact half-edge tables: GT[V][3] vertex positions, VT[H] origin vertex of half-edge,
+ *   OT[H] opposite half-edge or NIL, EVT[V] one outgoing half-edge per vertex (border half-edge for
+ *   border vertices, NIL for isolated vertices); H = 3 * faces.
+ *
+ * Parity contract: distances equal parallel_toplesets_propagation_cpu (src/geodesics_ptp.cpp:122-199)
+ * bit for bit (stronger than the stated 1e-5 / 1e-10 relative tolerance); toplesets / sorted / limits
+ * equal che::compute_toplesets (src/che.cpp:546-593) bit for bit.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device (sm_100a build).
+ * Nothing here calls cudaDeviceReset() (the reference does, src/cuda/geodesics_ptp.cu:22).
+ */
+#ifndef PTP_B200_H
+#define PTP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTP_NIL 0xFFFFFFFFu
+
+enum {
+    PTP_OK = 0,
+    PTP_ERR_INVALID = -1,   /* bad argument (null pointer, index out of range, sizes) */
+    PTP_ERR_CUDA = -2,      /* CUDA runtime / driver failure (text in ptp_last_error) */
+    PTP_ERR_CAPACITY = -3,  /* caller-provided output buffer too small */
+    PTP_ERR_MESH = -4,      /* mesh tables inconsistent (one-ring walk does not terminate) */
+    PTP_ERR_NO_DEVICE = -5  /* no CUDA device / kernel image not loadable on this device */
+};
+
+typedef struct ptp_mesh ptp_mesh_t; /* opaque device-resident mesh + solver workspace */
+
+/* per-call statistics; times are device times from CUDA events, milliseconds */
+typedef struct ptp_stats {
+    uint64_t n_reached;      /* limits.back(): vertices reached from the sources (duplicates counted)  */
+    uint64_t n_levels;       /* number of toplesets (= limits.size() - 1)                             */
+    uint64_t iterations;     /* PTP iterations executed (src/geodesics_ptp.cpp:145)                   */
+    uint64_t vertex_updates; /* sum over iterations of the window size limits[j] - limits[i]          */
+    uint64_t max_window;     /* largest window                                                        */
+    uint64_t gpu_launches;   /* kernels this call launched                                            */
+    double ms_toplesets;     /* BFS + topleset-order layout                                           */
+    double ms_solve;         /* relaxation sweep + scatter back to vertex order                       */
+    double ms_total;         /* first launch to last launch, device time                              */
+} ptp_stats_t;
+
+/* ------------------------------------------------------------------------------------------------ */
+
+const char *ptp_last_error(void);           /* thread-local text of the last failure               */
+int ptp_device_count(void);                 /* number of CUDA devices, <= 0 when none                */
+const char *ptp_version(void);
+
+/* pinned host memory helpers (optional; any host pointer is accepted by the entry points below) */
+void *ptp_host_alloc(size_t bytes);
+void ptp_host_free(void *p);
+
+/* Mesh upload. Replaces CHE::CHE(che*) + cuda_create_CHE (src/che.cpp:36-46, src/cuda/che.cu:29-48),
+ * which the reference repeats on every solve; here the mesh stays resident until ptp_mesh_destroy.
+ * Host tables are copied, the caller keeps ownership. Builds the per-vertex one-ring table on the
+ * device (the for_star order of include/che.h:10). `device` is a CUDA ordinal. */
+int ptp_mesh_create_f32(const float *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
+                        uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
+int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
+                        uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
+void ptp_mesh_destroy(ptp_mesh_t *mesh);
+uint64_t ptp_mesh_n_vertices(const ptp_mesh_t *mesh);
+uint64_t ptp_mesh_n_half_edges(const ptp_mesh_t *mesh);
+int ptp_mesh_real_size(const ptp_mesh_t *mesh); /* 4 or 8 */
+int ptp_mesh_device(const ptp_mesh_t *mesh);
+uint64_t ptp_mesh_device_bytes(const ptp_mesh_t *mesh); /* device memory currently held */
+
+/* Topleset construction on the device. Replaces che::compute_toplesets (src/che.cpp:546-593):
+ *   sorted[0..S) = sources in the given order (duplicates kept), level 0; BFS in queue order;
+ *   limits = [0, S, ..., p] one entry per level start plus the end; k caps the levels (PTP_NIL = no cap).
+ * Outputs (host; any may be NULL): toplesets[V] (NIL for unreached), sorted[sorted_capacity]
+ * (first limits.back() entries valid; needs V + number of duplicate sources), limits[limits_capacity].
+ * *n_limits receives limits.size(). */
+int ptp_toplesets(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources, uint32_t k,
+                  uint32_t *toplesets, uint32_t *sorted, uint64_t sorted_capacity,
+                  uint32_t *limits, uint64_t limits_capacity, uint32_t *n_limits, ptp_stats_t *stats);
+
+/* Solve with caller-provided toplesets. Replaces parallel_toplesets_propagation_gpu
+ * (src/cuda/geodesics_ptp.cu:20-85, declared include/geodesics_ptp.h:36) and
+ * parallel_toplesets_propagation_coalescence_gpu (src/cuda/geodesics_ptp_coalescence.cu:21-100,
+ * include/geodesics_ptp.h:34): ptp_out_t{dist, clusters} -> dist / clusters, toplesets_t{limits, index}
+ * -> limits / sorted. dist[V] receives the distances (INF for unreached). clusters may be NULL; when
+ * given it receives, for every reached vertex, 1 + the index of its nearest source (rule of
+ * src/cuda/geodesics_ptp.cu:277) and `cluster_fill` elsewhere. limits.size() < 3 performs no sweep
+ * (the reference reads limits[2] unconditionally). */
+int ptp_solve_f32(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources,
+                  const uint32_t *limits, uint32_t n_limits, const uint32_t *sorted,
+                  float *dist, uint32_t *clusters, uint32_t cluster_fill, ptp_stats_t *stats);
+int ptp_solve_f64(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources,
+                  const uint32_t *limits, uint32_t n_limits, const uint32_t *sorted,
+                  double *dist, uint32_t *clusters, uint32_t cluster_fill, ptp_stats_t *stats);
+
+/* Toplesets + solve in one device pipeline, nothing but the sources going up and the results coming
+ * down. Replaces geodesics::run_parallel_toplesets_propagation_gpu (src/geodesics.cpp:225-240), i.e.
+ * what `geodesics(mesh, sources, PTP_GPU, ...)` executes. sorted_index (may be NULL) receives the BFS
+ * order like geodesics::sorted_index (first n_reached entries, capacity sorted_capacity). */
+int ptp_geodesics_f32(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources,
+                      float *dist, uint32_t *clusters, uint32_t cluster_fill,
+                      uint32_t *sorted_index, uint64_t sorted_capacity, ptp_stats_t *stats);
+int ptp_geodesics_f64(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources,
+                      double *dist, uint32_t *clusters, uint32_t cluster_fill,
+                      uint32_t *sorted_index, uint64_t sorted_capacity, ptp_stats_t *stats);
+
+/* Batched independent solves (distance-matrix rows; the callers are sampling / key_components style
+ * loops such as src/sampling.cpp:23-34). Source set b is sources[offsets[b] .. offsets[b+1]); with
+ * offsets == NULL every source is its own single-source solve (n_batch = n_sources).
+ * rows receives n_batch rows of V reals (row-major). rows_on_device != 0 means `rows` is a device
+ * pointer on the mesh's device (used by the multi-GPU gather); otherwise a host pointer.
+ * `stream` is a cudaStream_t (NULL = the legacy default stream). */
+int ptp_solve_batched_f32(ptp_mesh_t *mesh, const uint32_t *sources, const uint64_t *offsets,
+                          uint32_t n_batch, uint64_t n_sources, float *rows, int rows_on_device,
+                          void *stream, ptp_stats_t *stats);
+int ptp_solve_batched_f64(ptp_mesh_t *mesh, const uint32_t *sources, const uint64_t *offsets,
+                          uint32_t n_batch, uint64_t n_sources, double *rows, int rows_on_device,
+                          void *stream, ptp_stats_t *stats);
+
+/* Farthest-point sampling on the resident mesh. Replaces farthest_point_sampling_ptp_gpu
+ * (src/cuda/geodesics_ptp.cu:87-172): starting from samples[0..n_initial), repeatedly solve from all
+ * samples so far and append the arg-max vertex (first maximum, like cublasI?amax) until n_total samples
+ * or max distance <= radio. samples must hold n_total entries; *n_out receives the final count,
+ * *max_dist the last maximum (INF if never read, as the reference). */
+int ptp_farthest_point_sampling_f32(ptp_mesh_t *mesh, uint32_t *samples, uint32_t n_initial, uint32_t n_total,
+                                    float radio, uint32_t *n_out, float *max_dist, ptp_stats_t *stats);
+int ptp_farthest_point_sampling_f64(ptp_mesh_t *mesh, uint32_t *samples, uint32_t n_initial, uint32_t n_total,
+                                    double radio, uint32_t *n_out, double *max_dist, ptp_stats_t *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTP_B200_H */

@@ -1,0 +1,46 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ptp_b200.h declares; the product path
+fails loudly (never falls back) when no device is present."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gproshan_b200 import _lib, api
+from gproshan_b200 import meshgen as mg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "ptp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    for s in header_symbols():
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.ptp_version()
+
+
+def test_no_cpu_fallback_without_device():
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.PtpError) as e:
+        api.DeviceMesh(mg.grid(6))
+    assert e.value.code == -5  # PTP_ERR_NO_DEVICE
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gproshan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_lib" not in src and "libptp_oracle" not in src and "orc_" not in src, f

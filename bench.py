@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""PTP geodesics benchmark (contract: one JSON line on stdout from rank 0).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                      # the reference's own CPU PTP on the host cores
+    torchrun ... bench.py --gpus N ...                        # one process per GPU (batched sources sharded)
+
+Workloads (BASELINE.json configs):
+  batched  C5: icosphere f=447 (1 998 092 vertices, float), independent single-source solves, 128 sources per
+           GPU (weak scaling: N=8 is the 1024-source distance-matrix job), rows gathered with one NCCL all_gather.
+           This is the line's `metric`/`value` at every N so the driver's scaling numbers compare like with like.
+  single   C3: noisy icosphere f=1000 (10 000 002 vertices, double), one source; reported on the N=1 line under
+           "single_source" (ms/solve, vertex-updates/s, its own roofline, e2e and CPU baseline).
+
+A step = one pass of the hot path: one batched call over this rank's sources (+ gather), or one solve.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE = {4: 72, 8: 92}  # 52 + 5*sizeof(real) algorithmic bytes per vertex-update
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+
+def workload_meshes(quick):
+    from gproshan_b200 import meshgen as mg
+    f5, f3 = (60, 100) if quick else (447, 1000)
+    return mg, f5, f3
+
+
+def build_c5(quick):
+    mg, f5, _ = workload_meshes(quick)
+    t = time.perf_counter()
+    mesh = mg.icosphere(f5, dtype=np.float32)
+    srcs = mg.random_sources(1024, 1024, mesh.n_vertices, unique=True)
+    log(f"[bench] C5 icosphere f={f5}: {mesh.n_vertices} vertices, {srcs.size} unique sources, built in {time.perf_counter()-t:.1f}s")
+    return mesh, srcs, f"C5 batched single-source solves, icosphere f={f5} V={mesh.n_vertices} float"
+
+
+def build_c3(quick):
+    mg, _, f3 = workload_meshes(quick)
+    t = time.perf_counter()
+    sigma = 0.2 * mg.mean_edge_icosphere(f3)
+    mesh = mg.icosphere(f3, noise_sigma=sigma, seed=12345, dtype=np.float64)
+    log(f"[bench] C3 noisy icosphere f={f3}: {mesh.n_vertices} vertices, sigma={sigma:.3e}, built in {time.perf_counter()-t:.1f}s")
+    return mesh, np.array([0], dtype=np.uint32), f"C3 single-source, noisy icosphere f={f3} V={mesh.n_vertices} double"
+
+
+def cpu_runner(dtype):
+    """The CPU arm: the reference's own code (oracle/_ref) when it was built, else the oracle port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    if ol.ref_available(dtype):
+        ref = ol.Reference(dtype)
+
+        def make(mesh):
+            rc = ref.che_raw(mesh)
+
+            def solve(src):
+                top, srt, lim = rc.compute_toplesets(src)
+                return rc.ptp_cpu(src, lim, srt), lim, srt
+            return solve
+        return "reference", make
+    orc = ol.Oracle()
+
+    def make(mesh):
+        def solve(src):
+            top, srt, lim = orc.compute_toplesets(mesh, src)
+            return orc.ptp_cpu(mesh, src, lim, srt)[0], lim, srt
+        return solve
+    return "port", make
+
+
+def cpu_sources_per_s(mesh, srcs, budget_s, max_n):
+    kind, make = cpu_runner(mesh.GT.dtype)
+    solve = make(mesh)
+    n, t0 = 0, time.perf_counter()
+    while n < max_n and (n == 0 or time.perf_counter() - t0 < budget_s):
+        solve(srcs[n:n + 1])
+        n += 1
+    dt = time.perf_counter() - t0
+    return kind, n, dt
+
+
+# ------------------------------------------------------------------------------------------------ arms
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU PTP (compute_toplesets + parallel_toplesets_propagation_cpu) on the
+    host cores, same config and metric. Rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    mesh, srcs, wl = build_c5(args.quick)
+    kind, make = cpu_runner(mesh.GT.dtype)
+    solve = make(mesh)
+    per_step = max(1, args.ref_sources_per_step)
+    k = 0
+    for _ in range(args.warmup):
+        solve(srcs[k:k + 1]); k += 1
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            solve(srcs[k % srcs.size:k % srcs.size + 1]); k += 1; done += 1
+        if time.perf_counter() - t0 > args.ref_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    steps_done = max(1, done // per_step)
+    val = done / dt
+    line = {
+        "impl": "reference", "metric": "ptp_batched_sources_per_s", "value": val, "unit": "sources/s", "n_gpus": args.gpus,
+        "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps_done, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "sources_per_step": per_step, "note": "CPU PTP on host cores; a step is a bounded sample of the batch"},
+        "cpu_baseline": {"value": val, "unit": "sources/s", "cores": cores, "kind": kind,
+                         "sample": f"{done} single-source solves (compute_toplesets + parallel_toplesets_propagation_cpu), OpenMP on {cores} threads"},
+        "e2e": {"value": val, "unit": "sources/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from gproshan_b200 import api
+
+    if not torch.cuda.is_available() or api.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — the PTP path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peak, peak_src = measured_peaks()
+
+    # ---------------- batched (the line's metric)
+    mesh, srcs_all, wl = build_c5(args.quick)
+    V = mesh.n_vertices
+    per_gpu = min(args.batch_per_gpu, srcs_all.size // world)
+    mine = np.ascontiguousarray(srcs_all[rank * per_gpu:(rank + 1) * per_gpu])
+    t = time.perf_counter()
+    dm = api.DeviceMesh(mesh, device=local_rank)
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t
+    rows = torch.empty((per_gpu, V), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((per_gpu * world, V), dtype=torch.float32, device="cuda") if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_resident():
+        dm.solve_batched(mine, rows_device_ptr=rows.data_ptr(), stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rows)
+        return dm.last_stats
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    kern_ms, updates, launches = [], 0, 0
+    for _ in range(args.steps):
+        st = step_resident()
+        kern_ms.append(st["ms_solve"]); updates = st["vertex_updates"]; launches += st["gpu_launches"]
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    upd = torch.tensor([float(updates)], device="cuda")
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(upd, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    ms_step = ms_total / args.steps
+    value = per_gpu * world / (ms_step / 1e3)
+
+    # e2e: host sources in, host rows out (pinned), every step
+    host_rows = torch.empty((per_gpu, V), dtype=torch.float32, pin_memory=True)
+    host_np = host_rows.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    dm.solve_batched(mine, rows=host_np)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        dm.solve_batched(mine, rows=host_np)
+        checksum = float(host_np[0, :8].sum())
+    e2e_s = torch.tensor([time.perf_counter() - t], device="cuda")
+    if dist:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = per_gpu * world * e2e_steps / float(e2e_s.item())
+
+    kernel_ms = statistics.mean(kern_ms)
+    achieved = updates * BYTES_PER_UPDATE[4] / (kernel_ms / 1e3) / 1e9
+    line = {
+        "metric": "ptp_batched_sources_per_s", "value": value, "unit": "sources/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "sources_per_gpu": per_gpu, "sources_total": per_gpu * world,
+                   "sharding": "sources block-partitioned, mesh replicated, one NCCL all_gather of the rows" if world > 1 else "single GPU",
+                   "l2": "per-solve working set ~150 MB x resident solves exceeds the 126 MB L2; no explicit flush",
+                   "vertex_updates_per_step_all_gpus": float(upd.item()), "mesh_upload_s": upload_s},
+        "vertex_updates_per_s": float(upd.item()) / (ms_step / 1e3),
+        "e2e": {"value": e2e_val, "unit": "sources/s", "h2d_bytes_per_step": int(mine.nbytes),
+                "d2h_bytes_per_step": int(host_np.nbytes), "steps": e2e_steps, "checksum": checksum},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_batched<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[4], "vertex_updates_per_launch": updates,
+                     "kernel_ms": kernel_ms,
+                     "note": "rank 0's kernel; includes BFS + layout + sweep of every source in the launch"},
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and args.workload in ("auto", "both", "single"):
+        line["single_source"] = run_single(args, api, torch, peak, peak_src)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, n, dt = cpu_sources_per_s(mesh, mine, args.cpu_budget_s, 16)
+        line["cpu_baseline"] = {"value": n / dt, "unit": "sources/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"{n} of the {per_gpu} sources of this workload, {dt:.1f}s, OpenMP on all host threads"}
+    dm.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_single(args, api, torch, peak, peak_src):
+    mesh, src, wl = build_c3(args.quick)
+    V = mesh.n_vertices
+    t = time.perf_counter()
+    dm = api.DeviceMesh(mesh, device=torch.cuda.current_device())
+    upload_s = time.perf_counter() - t
+    out = torch.empty(V, dtype=torch.float64, pin_memory=True).numpy()
+    steps = max(3, min(args.steps, 10))
+    for _ in range(max(1, min(args.warmup, 3))):
+        dm.geodesics(src, out=out)
+    dev_ms, top_ms, sol_ms, wall = [], [], [], []
+    for _ in range(steps):
+        t = time.perf_counter()
+        dm.geodesics(src, out=out)            # host sources in, host distances out: the e2e call
+        wall.append((time.perf_counter() - t) * 1e3)
+        st = dm.last_stats
+        dev_ms.append(st["ms_total"]); top_ms.append(st["ms_toplesets"]); sol_ms.append(st["ms_solve"])
+    st = dm.last_stats
+    ms = statistics.median(dev_ms)
+    sweep_ms = statistics.median(sol_ms)
+    achieved = st["vertex_updates"] * BYTES_PER_UPDATE[8] / (sweep_ms / 1e3) / 1e9
+    res = {
+        "workload": wl, "ms_per_solve": ms, "ms_toplesets_and_layout": statistics.median(top_ms), "ms_sweep": sweep_ms,
+        "vertex_updates": st["vertex_updates"], "iterations": st["iterations"], "levels": st["n_levels"],
+        "max_window": st["max_window"], "vertex_updates_per_s": st["vertex_updates"] / (ms / 1e3),
+        "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
+        "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],
+        "roofline": {"bound": "hbm", "kernel": "k_solve_grid<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[8],
+                     "note": "latency-bound by construction: ~#toplesets dependent iterations (SURVEY.md §0.4)"},
+    }
+    if not args.no_cpu_baseline:
+        kind, make = cpu_runner(np.float64)
+        solve = make(mesh)
+        t = time.perf_counter()
+        ref, lim, srt = solve(src)
+        cpu_s = time.perf_counter() - t
+        rel = np.abs(out - ref)[np.isfinite(ref)] / np.maximum(ref[np.isfinite(ref)], 1e-300)
+        res["cpu_baseline"] = {"value": cpu_s * 1e3, "unit": "ms/solve", "cores": os.cpu_count(), "kind": kind,
+                               "sample": "1 full solve (compute_toplesets + parallel_toplesets_propagation_cpu)"}
+        res["parity_vs_cpu"] = {"max_rel_err": float(rel.max()), "bit_equal": bool(np.array_equal(out, ref))}
+    dm.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "single", "batched", "both"])
+    ap.add_argument("--batch-per-gpu", type=int, default=128)
+    ap.add_argument("--quick", action="store_true", help="small meshes (smoke / CI)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--ref-sources-per-step", type=int, default=1)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus:
+            log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,8 @@ class PtpError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [("n_reached", C.c_uint64), ("n_levels", C.c_uint64), ("iterations", C.c_uint64),
-                ("vertex_updates", C.c_uint64), ("max_window", C.c_uint64), ("gpu_launches", C.c_uint64),
+                ("vertex_updates", C.c_uint64), ("max_window", C.c_uint64), ("relaxations", C.c_uint64),
+                ("gpu_launches", C.c_uint64),
                 ("ms_toplesets", C.c_double), ("ms_solve", C.c_double), ("ms_total", C.c_double)]
 
     def as_dict(self):

@@ -38,7 +38,9 @@ int fail(int code, const std::string &msg)
     } while (0)
 
 constexpr int GRID_BLOCK = 512;   // threads per CTA, cooperative (whole-GPU) kernels
-constexpr int BATCH_BLOCK = 512;  // threads per CTA, one-solve-per-CTA kernels
+template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
+template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
+template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; };
 constexpr int FLAT_BLOCK = 256;
 
 // ------------------------------------------------------------------------------------------------
@@ -120,6 +122,30 @@ __global__ void k_ring_build(const u32 *__restrict__ VT, const u32 *__restrict__
     }
 }
 
+// u in ring(v) must imply v in ring(u): the change-driven sweep stamps the ring of a vertex that moved and
+// relies on that ring containing every vertex that reads it. counters[2] counts violations.
+__global__ void k_ring_check(const u32 *__restrict__ ring8, const u32 *__restrict__ pool, u32 V, ull *counters)
+{
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    auto row_len = [&](const u32 *row) { u32 n = 0; while (n < GL && row[n] != NIL) n++; return n; };
+    auto get = [&](const u32 *row, bool ovf, u32 k) { return ovf ? pool[row[1] + k] : (k == 0 ? (row[0] & ~OPEN_BIT) : row[k]); };
+    const u32 *rv = ring8 + (size_t)v * GL;
+    const bool ov = rv[0] == OVF;
+    const u32 lv = ov ? rv[2] : row_len(rv);
+    u32 bad = 0;
+    for (u32 k = 0; k < lv; k++) {
+        const u32 n = get(rv, ov, k);
+        const u32 *rn = ring8 + (size_t)n * GL;
+        const bool on = rn[0] == OVF;
+        const u32 ln = on ? rn[2] : row_len(rn);
+        bool found = false;
+        for (u32 q = 0; q < ln && !found; q++) found = get(rn, on, q) == v;
+        if (!found) bad++;
+    }
+    if (bad) atomicAdd(counters + 2, (ull)bad);
+}
+
 struct TeamFlat { // plain grid-stride launch, no synchronisation
     static constexpr bool kGrid = false;
     __device__ __forceinline__ u32 cta() const { return blockIdx.x; }
@@ -161,17 +187,18 @@ k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u
 {
     TeamGrid t{bar, 0};
     const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-    const u32 d = ptp_run<R, TeamGrid, CL>(t, w, sources, S, nl, p);
+    const u32 d = ptp_run<R, TeamGrid, CL, 8>(t, w, sources, S, nl, p, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
 }
 
 // one CTA per solve, CTAs pull source sets from a queue
 template <class R>
-__global__ void __launch_bounds__(BATCH_BLOCK)
+__global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
 k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, ull *queue,
           ull *totals)
 {
     __shared__ u32 s_b;
+    __shared__ u32 s_wl[2];
     TeamCta t;
     const Work<R> w = works[blockIdx.x];
     while (true) {
@@ -183,11 +210,11 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
         const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
         const u32 *src = sources + o0;
-        if (threadIdx.x == 0) w.ctrl[C_OVFALLOC] = 0;
+        if (threadIdx.x == 0) { w.ctrl[C_OVFALLOC] = 0; w.ctrl[C_RELAXED] = 0; }
         bfs_run<R, TeamCta>(t, m, w, src, S, NIL);
         const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
         layout_run<R, TeamCta>(t, m, w, p);
-        const u32 d = ptp_run<R, TeamCta, false>(t, w, src, S, nl, p);
+        const u32 d = ptp_run<R, TeamCta, false, 1>(t, w, src, S, nl, p, s_wl, m.ring_symmetric != 0);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -196,6 +223,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
             atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
             atomicAdd(totals + 3, (ull)(nl ? nl - 1 : 0));
             atomicAdd(totals + 4, (ull)p);
+            atomicAdd(totals + 5, w.ctrl[C_RELAXED]);
         }
     }
 }
@@ -248,6 +276,7 @@ struct ptp_mesh {
     u64 V = 0, H = 0;
     int num_sms = 0;
     void *GT4 = nullptr;
+    bool ring_symmetric = true;
     u32 *ring8 = nullptr;
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
@@ -262,7 +291,7 @@ struct ptp_mesh {
     void *w_key = nullptr, *w_sorted = nullptr, *w_inv = nullptr, *w_limits = nullptr, *w_tile = nullptr, *w_posS = nullptr,
          *w_ringS = nullptr, *w_ovfS = nullptr, *w_dist[2] = {nullptr, nullptr}, *w_cl[2] = {nullptr, nullptr},
          *w_top = nullptr, *w_ctrl = nullptr, *w_bar = nullptr, *w_src = nullptr, *w_out = nullptr, *w_clout = nullptr,
-         *w_maxval = nullptr;
+         *w_maxval = nullptr, *w_wl = nullptr, *w_dirty[2] = {nullptr, nullptr};
     void *h_ctrl = nullptr; // pinned
 
     // batched workspace (lazy)
@@ -296,6 +325,7 @@ template <class R> MeshView<R> mesh_view(const ptp_mesh *m)
 {
     MeshView<R> v;
     v.V = (u32)m->V;
+    v.ring_symmetric = m->ring_symmetric ? 1u : 0u;
     v.GT4 = (const typename Ops<R>::vec4 *)m->GT4;
     v.ring8 = m->ring8;
     v.ovf = m->ovf;
@@ -317,6 +347,9 @@ template <class R> Work<R> work_view(const ptp_mesh *m)
     w.dist[1] = (R *)m->w_dist[1];
     w.cl[0] = (u32 *)m->w_cl[0];
     w.cl[1] = (u32 *)m->w_cl[1];
+    w.wl = (u32 *)m->w_wl;
+    w.dirty[0] = (unsigned char *)m->w_dirty[0];
+    w.dirty[1] = (unsigned char *)m->w_dirty[1];
     w.toplesets = nullptr;
     w.ctrl = (ull *)m->w_ctrl;
     return w;
@@ -345,6 +378,9 @@ template <class R> int ensure_workspace(ptp_mesh *m, u64 S, bool need_cl, bool n
     WS(m->w_ovfS, 4 * std::max<u64>(m->ovf_total, 4))
     WS(m->w_dist[0], sizeof(R) * (N + 1))
     WS(m->w_dist[1], sizeof(R) * (N + 1))
+    WS(m->w_wl, 4 * N)
+    WS(m->w_dirty[0], N + 1)
+    WS(m->w_dirty[1], N + 1)
     if (cl) {
         WS(m->w_cl[0], 4 * (N + 1))
         WS(m->w_cl[1], 4 * (N + 1))
@@ -443,6 +479,7 @@ void fill_stats(const ptp_mesh *m, ptp_stats_t *st, u64 launches, double ms_top,
     st->iterations = c[C_ITER];
     st->vertex_updates = c[C_UPDATES];
     st->max_window = c[C_MAXWIN];
+    st->relaxations = c[C_RELAXED];
     st->gpu_launches = launches;
     st->ms_toplesets = ms_top;
     st->ms_solve = ms_solve;
@@ -489,7 +526,7 @@ int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V
     CKM(cudaMalloc(&d_vt, 4 * H));
     CKM(cudaMalloc(&d_ot, 4 * H));
     CKM(cudaMalloc(&d_evt, 4 * V));
-    CKM(cudaMalloc(&d_cnt, 16));
+    CKM(cudaMalloc(&d_cnt, 32));
     auto free_tmp = [&]() {
         cudaFree(d_gt); cudaFree(d_vt); cudaFree(d_ot); cudaFree(d_evt); cudaFree(d_cnt);
     };
@@ -502,7 +539,7 @@ int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V
     CKT(cudaMemcpyAsync(d_vt, VT, 4 * H, cudaMemcpyHostToDevice, m->stream));
     CKT(cudaMemcpyAsync(d_ot, OT, 4 * H, cudaMemcpyHostToDevice, m->stream));
     CKT(cudaMemcpyAsync(d_evt, EVT, 4 * V, cudaMemcpyHostToDevice, m->stream));
-    CKT(cudaMemsetAsync(d_cnt, 0, 16, m->stream));
+    CKT(cudaMemsetAsync(d_cnt, 0, 32, m->stream));
 
     if ((rc = dev_alloc(m, &m->GT4, sizeof(R) * 4 * V, nullptr))) { free_tmp(); return bail(rc); }
     if ((rc = dev_alloc(m, (void **)&m->ring8, 4 * GL * V, nullptr))) { free_tmp(); return bail(rc); }
@@ -525,6 +562,12 @@ int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V
         CKT(cudaGetLastError());
         CKT(cudaStreamSynchronize(m->stream));
     }
+    k_ring_check<<<(unsigned)((V + 127) / 128), 128, 0, m->stream>>>(m->ring8, m->ovf, (u32)V, (ull *)d_cnt);
+    CKT(cudaGetLastError());
+    ull asym[4] = {0, 0, 0, 0};
+    CKT(cudaMemcpyAsync(asym, d_cnt, 32, cudaMemcpyDeviceToHost, m->stream));
+    CKT(cudaStreamSynchronize(m->stream));
+    m->ring_symmetric = asym[2] == 0;
     free_tmp();
 #undef CKT
 #undef CKM
@@ -658,13 +701,13 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
         free_list(m, m->bt_allocs);
         m->bt_slots = 0;
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R>, BATCH_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R>, BatchCfg<R>::BLOCK, 0));
         if (per_sm < 1) return fail(PTP_ERR_CUDA, "batched kernel does not fit on an SM");
         const u32 slots = (u32)(m->num_sms * per_sm);
         const u64 V = m->V, scap = std::max<u64>(max_s, 16), N = V + scap;
         std::vector<Work<R>> hw(slots);
         auto &tr = m->bt_allocs;
-        char *b_key, *b_sorted, *b_inv, *b_limits, *b_tile, *b_pos, *b_ring, *b_ovf, *b_d0, *b_d1, *b_ctrl;
+        char *b_key, *b_sorted, *b_inv, *b_limits, *b_tile, *b_pos, *b_ring, *b_ovf, *b_d0, *b_d1, *b_ctrl, *b_wl, *b_q0, *b_q1;
         const u64 ovfn = std::max<u64>(m->ovf_total, 4);
 #define BT(ptr, per)                                                                     \
     if ((rc = dev_alloc(m, (void **)&(ptr), (u64)(per) * slots, &tr)) != PTP_OK) return rc;
@@ -679,6 +722,9 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
         BT(b_d0, sizeof(R) * (N + 1))
         BT(b_d1, sizeof(R) * (N + 1))
         BT(b_ctrl, 8 * C_COUNT)
+        BT(b_wl, 4 * N)
+        BT(b_q0, (N + 1 + 15) / 16 * 16)
+        BT(b_q1, (N + 1 + 15) / 16 * 16)
 #undef BT
         for (u32 s = 0; s < slots; s++) {
             Work<R> &w = hw[s];
@@ -695,6 +741,9 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
             w.cl[0] = w.cl[1] = nullptr;
             w.toplesets = nullptr;
             w.ctrl = (ull *)(b_ctrl + (u64)s * 8 * C_COUNT);
+            w.wl = (u32 *)(b_wl + (u64)s * 4 * N);
+            w.dirty[0] = (unsigned char *)(b_q0 + (u64)s * ((N + 1 + 15) / 16 * 16));
+            w.dirty[1] = (unsigned char *)(b_q1 + (u64)s * ((N + 1 + 15) / 16 * 16));
         }
         if ((rc = dev_alloc(m, &m->bt_works, sizeof(Work<R>) * slots, &tr))) return rc;
         if ((rc = dev_alloc(m, &m->bt_queue, 64, &tr))) return rc;
@@ -757,7 +806,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         R *dst = on_device ? rows + first * m->V : (R *)m->bt_rows;
         CK(cudaMemsetAsync(queue, 0, 8, stream));
         const u32 grid = std::min<u32>(m->bt_slots, nb);
-        k_batched<R><<<grid, BATCH_BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
+        k_batched<R><<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
                                                         offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst, queue,
                                                         queue + 1);
         CK(cudaGetLastError());
@@ -775,6 +824,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         st->max_window = tot[3];
         st->n_levels = tot[4];
         st->n_reached = tot[5];
+        st->relaxations = tot[6];
         st->gpu_launches = launches;
         st->ms_toplesets = 0;
         st->ms_solve = st->ms_total = ev_ms(m->ev[0], m->ev[1]);

@@ -48,6 +48,8 @@ typedef struct ptp_stats {
     uint64_t iterations;     /* PTP iterations executed (src/geodesics_ptp.cpp:145)                   */
     uint64_t vertex_updates; /* sum over iterations of the window size limits[j] - limits[i]          */
     uint64_t max_window;     /* largest window                                                        */
+    uint64_t relaxations;    /* one-ring relaxations actually executed (<= vertex_updates: vertices whose  *
+                              * inputs did not change since they were last relaxed keep their stored value) */
     uint64_t gpu_launches;   /* kernels this call launched                                            */
     double ms_toplesets;     /* BFS + topleset-order layout                                           */
     double ms_solve;         /* relaxation sweep + scatter back to vertex order                       */

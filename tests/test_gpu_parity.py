@@ -107,6 +107,41 @@ def test_batched_rows(dtype, oracle, gpu):
     assert stats["vertex_updates"] == upd
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_wide_windows_whole_gpu(dtype, oracle, gpu):
+    """torus whose band blows up (max window > 100k): exercises the compacted (sparse) iterations of the whole-GPU
+    sweep and the change-driven skipping; still bit-equal, and far fewer relaxations than vertex-updates."""
+    m = mg.torus(600, 300).astype(dtype)
+    src = [17]
+    t0, s0, l0 = oracle.compute_toplesets(m, src)
+    want, want_cl, st = oracle.ptp_cpu(m, src, l0, s0, clusters=True)
+    assert st["max_window"] > 60000
+    with api.DeviceMesh(m, gpu) as dm:
+        got, _, _ = dm.geodesics(src)
+        stats = dict(dm.last_stats)
+        got_c, cl, _ = dm.geodesics(src, clusters=True)
+    assert_dist_parity(got, want, dtype, "torus 600x300")
+    assert_dist_parity(got_c, want, dtype, "torus 600x300 (clusters variant)")
+    assert np.array_equal(cl, want_cl)
+    assert stats["iterations"] == st["iterations"] and stats["vertex_updates"] == st["vertex_updates"]
+    assert 0 < stats["relaxations"] < stats["vertex_updates"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_wide_windows_batched(dtype, oracle, gpu):
+    """one CTA per solve with windows far wider than the CTA (compacted iterations of the batched kernel)"""
+    m = mg.torus(240, 120).astype(dtype)
+    srcs = np.array([17, 5000, 28799, 12345], dtype=np.uint32)
+    with api.DeviceMesh(m, gpu) as dm:
+        rows = dm.solve_batched(srcs)
+        stats = dict(dm.last_stats)
+    assert stats["max_window"] > 4096 and stats["relaxations"] < stats["vertex_updates"]
+    for b, s in enumerate(srcs):
+        t0, s0, l0 = oracle.compute_toplesets(m, [s])
+        want, _, _ = oracle.ptp_cpu(m, [s], l0, s0)
+        assert_dist_parity(rows[b], want, dtype, f"row {b}")
+
+
 def test_batched_source_sets(oracle, gpu):
     m = mg.torus(48, 20).astype(np.float32)
     sets = [[1, 500], [77], [3, 3, 900, 20], [959]]

@@ -202,8 +202,9 @@ def run_b200(args, rank, world, local_rank):
     # ---------------- batched (the line's metric)
     mesh, srcs_all, wl = build_c5(args.quick)
     V = mesh.n_vertices
+    from gproshan_b200.sharding import gather_rows, shard_sources
     per_gpu = min(args.batch_per_gpu, srcs_all.size // world)
-    mine = np.ascontiguousarray(srcs_all[rank * per_gpu:(rank + 1) * per_gpu])
+    mine = np.ascontiguousarray(shard_sources(srcs_all, rank, world, per_rank=per_gpu))
     t = time.perf_counter()
     dm = api.DeviceMesh(mesh, device=local_rank)
     torch.cuda.synchronize()
@@ -215,7 +216,7 @@ def run_b200(args, rank, world, local_rank):
     def step_resident():
         dm.solve_batched(mine, rows_device_ptr=rows.data_ptr(), stream=stream)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rows)
+            gather_rows(rows, world, out=gathered)
         return dm.last_stats
 
     for _ in range(args.warmup):
@@ -280,7 +281,7 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "k_batched<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[4], "vertex_updates_per_launch": updates,
-                     "kernel_ms": kernel_ms,
+                     "relaxations_per_launch": st["relaxations"], "kernel_ms": kernel_ms,
                      "note": "rank 0's kernel; includes BFS + layout + sweep of every source in the launch"},
         "clocks": clocks,
     }
@@ -322,7 +323,7 @@ def run_single(args, api, torch, peak, peak_src):
     achieved = st["vertex_updates"] * BYTES_PER_UPDATE[8] / (sweep_ms / 1e3) / 1e9
     res = {
         "workload": wl, "ms_per_solve": ms, "ms_toplesets_and_layout": statistics.median(top_ms), "ms_sweep": sweep_ms,
-        "vertex_updates": st["vertex_updates"], "iterations": st["iterations"], "levels": st["n_levels"],
+        "vertex_updates": st["vertex_updates"], "relaxations": st["relaxations"], "iterations": st["iterations"], "levels": st["n_levels"],
         "max_window": st["max_window"], "vertex_updates_per_s": st["vertex_updates"] / (ms / 1e3),
         "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
         "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],

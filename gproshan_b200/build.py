@@ -62,10 +62,18 @@ def build_oracle(force=False):
     _run(["make", "-C", odir] + (["-B"] if force else []))
 
 
+def build_shim(force=False):
+    """The C++ drop-in (reference signatures) linked against the reference's own CPU sources, for the tests.
+    Only possible where /root/reference exists; the built .so travels to the GPU box."""
+    sdir = os.path.join(HERE, "shim")
+    _run(["make", "-C", sdir] + (["-B"] if force else []))
+
+
 def build_all(force=False, verbose=False):
     build_meshgen(force)
     build_cuda(force, verbose)
     build_oracle(force)
+    build_shim(force)
 
 
 if __name__ == "__main__":

@@ -37,7 +37,8 @@ int fail(int code, const std::string &msg)
         }                                                                                                     \
     } while (0)
 
-constexpr int GRID_BLOCK = 512;   // threads per CTA, cooperative (whole-GPU) kernels
+constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
+constexpr int SOLVE_BLOCK = 1024;  // threads per CTA, cooperative sweep kernel (one pass per iteration on C3-size windows)
 template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
 template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
 template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; };
@@ -182,7 +183,7 @@ template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshVi
 }
 
 template <class R, bool CL>
-__global__ void __launch_bounds__(GRID_BLOCK)
+__global__ void __launch_bounds__(SOLVE_BLOCK)
 k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, ull *bar)
 {
     TeamGrid t{bar, 0};
@@ -458,7 +459,7 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     Work<R> w = work_view<R>(m);
     int grid;
     void *fn = cl ? (void *)k_solve_grid<R, true> : (void *)k_solve_grid<R, false>;
-    int rc = cl ? coop_grid(k_solve_grid<R, true>, GRID_BLOCK, m, &grid) : coop_grid(k_solve_grid<R, false>, GRID_BLOCK, m, &grid);
+    int rc = cl ? coop_grid(k_solve_grid<R, true>, SOLVE_BLOCK, m, &grid) : coop_grid(k_solve_grid<R, false>, SOLVE_BLOCK, m, &grid);
     if (rc) return rc;
     const u32 *src = (const u32 *)m->w_src;
     R *out = (R *)m->w_out;
@@ -466,7 +467,7 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     ull *bar = (ull *)m->w_bar;
     void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &bar};
     CK(cudaMemsetAsync(m->w_bar, 0, 64, m->stream));
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GRID_BLOCK), args, 0, m->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_BLOCK), args, 0, m->stream));
     return PTP_OK;
 }
 

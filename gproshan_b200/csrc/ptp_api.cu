@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -38,6 +39,7 @@ int fail(int code, const std::string &msg)
     } while (0)
 
 constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
+constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
 constexpr int SOLVE_BLOCK = 1024;  // threads per CTA, cooperative sweep kernel (one pass per iteration on C3-size windows)
 template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
 template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
@@ -156,10 +158,10 @@ struct TeamFlat { // plain grid-stride launch, no synchronisation
 };
 
 template <class R>
-__global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 kcap, ull *bar)
+__global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 kcap, u32 sent, ull *bar)
 {
-    TeamGrid t{bar, 0};
-    bfs_run<R, TeamGrid>(t, m, w, sources, S, kcap);
+    TeamGrid t{bar, 0, 0, gridDim.x};
+    bfs_run<R, TeamGrid, false>(t, m, w, sources, S, kcap, sent);
 }
 
 template <class R> __global__ void k_inv_init(MeshView<R> m, Work<R> w)
@@ -176,27 +178,47 @@ template <class R> __global__ void k_inv_fill(MeshView<R> m, Work<R> w, u32 p)
     }
 }
 
-template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshView<R> m, Work<R> w)
+template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshView<R> m, Work<R> w, u32 sent)
 {
     TeamFlat t;
-    layout_run<R, TeamFlat>(t, m, w, (u32)w.ctrl[C_REACHED]);
+    layout_run<R, TeamFlat>(t, m, w, (u32)w.ctrl[C_REACHED], sent);
 }
 
 template <class R, bool CL>
 __global__ void __launch_bounds__(SOLVE_BLOCK)
-k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, ull *bar)
+k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar)
 {
-    TeamGrid t{bar, 0};
+    TeamGrid t{bar, 0, 0, gridDim.x};
     const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-    const u32 d = ptp_run<R, TeamGrid, CL, 8>(t, w, sources, S, nl, p, w.tile_sum + 2048, m.ring_symmetric != 0);
+    const u32 d = ptp_run<R, TeamGrid, CL, 8, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
+}
+
+// Single solve, one cooperative launch, two teams: CTAs [0, nb) build the toplesets and lay out the rows
+// (producer), CTAs [nb, gridDim) sweep behind them (consumer). The BFS (~#levels dependent steps) and the sweep
+// (~#levels dependent iterations) overlap instead of adding up.
+template <class R, bool CL>
+__global__ void __launch_bounds__(FUSED_BLOCK, 2)
+k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb)
+{
+    if (blockIdx.x < nb) {
+        TeamGrid t{bar, 0, 0, nb};
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
+        bfs_run<R, TeamGrid, true>(t, m, w, sources, S, NIL, sent);
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
+    } else {
+        TeamGrid t{bar + 64, 0, nb, gridDim.x - nb};
+        const u32 d = ptp_run<R, TeamGrid, CL, 8, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+        scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
+        if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
+    }
 }
 
 // one CTA per solve, CTAs pull source sets from a queue
 template <class R>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
-k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, ull *queue,
-          ull *totals)
+k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
+          ull *queue, ull *totals)
 {
     __shared__ u32 s_b;
     __shared__ u32 s_wl[2];
@@ -212,10 +234,10 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
         const u32 *src = sources + o0;
         if (threadIdx.x == 0) { w.ctrl[C_OVFALLOC] = 0; w.ctrl[C_RELAXED] = 0; }
-        bfs_run<R, TeamCta>(t, m, w, src, S, NIL);
+        bfs_run<R, TeamCta, false>(t, m, w, src, S, NIL, sent);
         const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-        layout_run<R, TeamCta>(t, m, w, p);
-        const u32 d = ptp_run<R, TeamCta, false, 1>(t, w, src, S, nl, p, s_wl, m.ring_symmetric != 0);
+        layout_run<R, TeamCta>(t, m, w, p, sent);
+        const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -391,7 +413,7 @@ template <class R> int ensure_workspace(ptp_mesh *m, u64 S, bool need_cl, bool n
     }
     if (top) { WS(m->w_top, 4 * V) } else m->w_top = nullptr;
     WS(m->w_ctrl, 8 * C_COUNT)
-    WS(m->w_bar, 8 * 8)
+    WS(m->w_bar, 1024)
     WS(m->w_src, 4 * scap)
     WS(m->w_out, sizeof(R) * V)
     WS(m->w_maxval, 16)
@@ -437,8 +459,9 @@ template <class R> int launch_bfs(ptp_mesh *m, u32 S, u32 kcap, bool want_top)
     if (rc) return rc;
     const u32 *src = (const u32 *)m->w_src;
     ull *bar = (ull *)m->w_bar;
-    void *args[] = {&mv, &w, &src, &S, &kcap, &bar};
-    CK(cudaMemsetAsync(m->w_bar, 0, 64, m->stream));
+    u32 sent = (u32)(m->V + m->ws_scap);
+    void *args[] = {&mv, &w, &src, &S, &kcap, &sent, &bar};
+    CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
     CK(cudaLaunchCooperativeKernel((void *)k_bfs_grid<R>, dim3(grid), dim3(GRID_BLOCK), args, 0, m->stream));
     return PTP_OK;
 }
@@ -448,7 +471,7 @@ template <class R> int launch_layout(ptp_mesh *m)
     MeshView<R> mv = mesh_view<R>(m);
     Work<R> w = work_view<R>(m);
     const int grid = m->num_sms * 8;
-    k_layout<R><<<grid, FLAT_BLOCK, 0, m->stream>>>(mv, w);
+    k_layout<R><<<grid, FLAT_BLOCK, 0, m->stream>>>(mv, w, (u32)(m->V + m->ws_scap));
     CK(cudaGetLastError());
     return PTP_OK;
 }
@@ -465,9 +488,46 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     R *out = (R *)m->w_out;
     u32 *clo = (u32 *)m->w_clout;
     ull *bar = (ull *)m->w_bar;
-    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &bar};
-    CK(cudaMemsetAsync(m->w_bar, 0, 64, m->stream));
+    u32 sent = (u32)(m->V + m->ws_scap);
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar};
+    CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
     CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_BLOCK), args, 0, m->stream));
+    return PTP_OK;
+}
+
+// number of CTAs given to the BFS/layout team of the fused single-solve kernel (PTP_BFS_CTAS overrides)
+int bfs_ctas(const ptp_mesh *m)
+{
+    static int env = [] { const char *e = getenv("PTP_BFS_CTAS"); return e ? atoi(e) : 0; }();
+    int nb = env > 0 ? env : m->num_sms; // default: one BFS CTA and one sweep CTA per SM
+    return std::max(1, std::min(nb, 2 * m->num_sms - 1));
+}
+
+bool use_fused()
+{
+    static int v = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
+
+template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
+{
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    if (!cl) w.cl[0] = w.cl[1] = nullptr;
+    void *fn = cl ? (void *)k_geodesics_fused<R, true> : (void *)k_geodesics_fused<R, false>;
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FUSED_BLOCK, 0));
+    if (per_sm < 2) return fail(PTP_ERR_CUDA, "fused kernel needs two resident CTAs per SM");
+    const int grid = 2 * m->num_sms;
+    const u32 *src = (const u32 *)m->w_src;
+    R *out = (R *)m->w_out;
+    u32 *clo = (u32 *)m->w_clout;
+    ull *bar = (ull *)m->w_bar;
+    u32 sent = (u32)(m->V + m->ws_scap);
+    u32 nb = (u32)bfs_ctas(m);
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb};
+    CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FUSED_BLOCK), args, 0, m->stream));
     return PTP_OK;
 }
 
@@ -662,6 +722,12 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     int rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
+    if (use_fused()) {
+        if ((rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        return PTP_OK;
+    }
     if ((rc = launch_bfs<R>(m, S, NIL, false))) return rc;
     if ((rc = launch_layout<R>(m))) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
@@ -689,7 +755,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
     }
     if ((rc = fetch_ctrl(m))) return rc;
-    fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    if (use_fused()) {
+        // one launch: the producer / consumer split comes from %globaltimer stamps written by the kernel
+        const ull *c = (const ull *)m->h_ctrl;
+        const double t_bfs = c[C_TBFS] > c[C_TSTART] ? (c[C_TBFS] - c[C_TSTART]) * 1e-6 : 0.0;
+        const double t_all = ev_ms(m->ev[0], m->ev[2]);
+        fill_stats(m, st, 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
+    } else
+        fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     if (sorted_index && scap < ((const ull *)m->h_ctrl)[C_REACHED])
         return fail(PTP_ERR_CAPACITY, "sorted_index buffer too small (needs V + duplicate sources)");
     return PTP_OK;
@@ -808,8 +881,8 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         CK(cudaMemsetAsync(queue, 0, 8, stream));
         const u32 grid = std::min<u32>(m->bt_slots, nb);
         k_batched<R><<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
-                                                        offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst, queue,
-                                                        queue + 1);
+                                                        offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
+                                                        (u32)(m->V + m->bt_scap), queue, queue + 1);
         CK(cudaGetLastError());
         launches++;
         if (!on_device)

@@ -232,7 +232,7 @@ def run_b200(args, rank, world, local_rank):
     kern_ms, updates, launches = [], 0, 0
     for _ in range(args.steps):
         st = step_resident()
-        kern_ms.append(st["ms_solve"]); updates = st["vertex_updates"]; launches += st["gpu_launches"]
+        kern_ms.append(st["ms_total"]); updates = st["vertex_updates"]; launches += st["gpu_launches"]
     e1.record()
     torch.cuda.synchronize()
     if dist:

@@ -234,13 +234,20 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
         const u32 *src = sources + o0;
         if (threadIdx.x == 0) { w.ctrl[C_OVFALLOC] = 0; w.ctrl[C_RELAXED] = 0; }
+        const ull t0 = global_timer();
         bfs_run<R, TeamCta, false>(t, m, w, src, S, NIL, sent);
+        const ull t1 = global_timer();
         const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
         layout_run<R, TeamCta>(t, m, w, p, sent);
+        const ull t2 = global_timer();
         const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
+            const ull t3 = global_timer();
+            atomicAdd(totals + 6, t1 - t0); // per-phase device time summed over solves (ns)
+            atomicAdd(totals + 7, t2 - t1);
+            atomicAdd(totals + 8, t3 - t2);
             atomicAdd(totals + 0, w.ctrl[C_ITER]);
             atomicAdd(totals + 1, w.ctrl[C_UPDATES]);
             atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
@@ -820,7 +827,7 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
             w.dirty[1] = (unsigned char *)(b_q1 + (u64)s * ((N + 1 + 15) / 16 * 16));
         }
         if ((rc = dev_alloc(m, &m->bt_works, sizeof(Work<R>) * slots, &tr))) return rc;
-        if ((rc = dev_alloc(m, &m->bt_queue, 64, &tr))) return rc;
+        if ((rc = dev_alloc(m, &m->bt_queue, 128, &tr))) return rc;
         CK(cudaMemcpy(m->bt_works, hw.data(), sizeof(Work<R>) * slots, cudaMemcpyHostToDevice));
         m->bt_slots = slots;
         m->bt_scap = scap;
@@ -871,7 +878,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     CK(cudaMemcpyAsync(m->bt_src, sources, 4 * n_src, cudaMemcpyHostToDevice, stream));
     if (offsets) CK(cudaMemcpyAsync(m->bt_off, offsets, 8 * (u64)(B + 1), cudaMemcpyHostToDevice, stream));
     ull *queue = (ull *)m->bt_queue;
-    CK(cudaMemsetAsync(queue, 0, 64, stream));
+    CK(cudaMemsetAsync(queue, 0, 128, stream));
     CK(cudaEventRecord(m->ev[0], stream));
     MeshView<R> mv = mesh_view<R>(m);
     u64 launches = 0;
@@ -889,8 +896,8 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
             CK(cudaMemcpyAsync(rows + first * m->V, m->bt_rows, sizeof(R) * (u64)nb * m->V, cudaMemcpyDeviceToHost, stream));
     }
     CK(cudaEventRecord(m->ev[1], stream));
-    ull tot[8];
-    CK(cudaMemcpyAsync(tot, queue, 64, cudaMemcpyDeviceToHost, stream));
+    ull tot[16];
+    CK(cudaMemcpyAsync(tot, queue, 128, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     if (st) {
         st->iterations = tot[1];
@@ -900,8 +907,11 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         st->n_reached = tot[5];
         st->relaxations = tot[6];
         st->gpu_launches = launches;
-        st->ms_toplesets = 0;
-        st->ms_solve = st->ms_total = ev_ms(m->ev[0], m->ev[1]);
+        // CTA-time spent in BFS + layout, and in the sweep, averaged over the CTAs that ran (device timers)
+        const double ctas = (double)std::min<u64>(m->bt_slots, B);
+        st->ms_toplesets = (double)(tot[7] + tot[8]) * 1e-6 / ctas;
+        st->ms_solve = (double)tot[9] * 1e-6 / ctas;
+        st->ms_total = ev_ms(m->ev[0], m->ev[1]);
     }
     return PTP_OK;
 }

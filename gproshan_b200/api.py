@@ -39,6 +39,26 @@ def device_count() -> int:
     return _lib.lib().ptp_device_count()
 
 
+def che_build(faces, n_vertices: int, device: int = 0):
+    """OT / EVT from a face list on the GPU (che::update_evt_ot_et, src/che.cpp:1295-1362).
+    -> (OT, EVT, manifold, device_ms)"""
+    VT = _u32(faces).reshape(-1)
+    OT = np.empty_like(VT)
+    EVT = np.empty(n_vertices, dtype=np.uint32)
+    mf, ms = C.c_int(), C.c_double()
+    check(_lib.lib().ptp_che_build(_p(VT), n_vertices, VT.size, _p(OT), _p(EVT), device, C.byref(mf), C.byref(ms)))
+    return OT, EVT, bool(mf.value), ms.value
+
+
+class FaceMesh:
+    """A bare face list + positions: DeviceMesh(FaceMesh(xyz, faces)) builds OT / EVT on the device."""
+
+    def __init__(self, xyz, faces):
+        self.GT = np.asarray(xyz)
+        self.VT = _u32(faces).reshape(-1)
+        self.OT = self.EVT = None
+
+
 class DeviceMesh:
     """A CHE mesh resident on one GPU (replaces the per-call CHE(mesh) + cuda_create_CHE upload,
     src/che.cpp:36-46, src/cuda/che.cu:29-48). Accepts anything with GT / VT / OT / EVT arrays."""
@@ -50,8 +70,10 @@ class DeviceMesh:
         if self.dtype not in _SUF:
             raise TypeError("real_t must be float32 or float64")
         GT = np.ascontiguousarray(GT, dtype=self.dtype)
-        VT, OT, EVT = _u32(mesh.VT), _u32(mesh.OT), _u32(mesh.EVT)
-        if GT.ndim != 2 or GT.shape[1] != 3 or OT.shape != VT.shape or EVT.shape[0] != GT.shape[0]:
+        VT = _u32(mesh.VT)
+        OT = None if mesh.OT is None else _u32(mesh.OT)
+        EVT = None if mesh.EVT is None else _u32(mesh.EVT)
+        if GT.ndim != 2 or GT.shape[1] != 3 or (OT is not None and (OT.shape != VT.shape or EVT.shape[0] != GT.shape[0])):
             raise ValueError("inconsistent CHE table shapes")
         self.n_vertices, self.n_half_edges = GT.shape[0], VT.shape[0]
         self.suf, self.ct = _SUF[self.dtype], _CT[self.dtype]

@@ -149,6 +149,67 @@ __global__ void k_ring_check(const u32 *__restrict__ ring8, const u32 *__restric
     if (bad) atomicAdd(counters + 2, (ull)bad);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CHE construction on the device (reference: che::update_evt_ot_et, src/che.cpp:1295-1362, serial, ~22 s at
+// 10 M vertices). Directed edges (a -> b) go into an open-addressing hash table keyed by (a << 32 | b);
+// OT[he] is the half-edge stored under (b, a). For edge-manifold input (every directed edge once) this is the
+// reference's pairing exactly; duplicates / multiple border half-edges at a vertex raise the non-manifold flag.
+
+__device__ __forceinline__ u32 edge_hash(ull k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (u32)k;
+}
+
+__global__ void k_che_insert(const u32 *__restrict__ VT, u32 H, u32 V, ull *keys, u32 *vals, u32 mask, u32 *evt1, ull *flags)
+{
+    const u32 he = blockIdx.x * blockDim.x + threadIdx.x;
+    if (he >= H) return;
+    const u32 a = VT[he], b = VT[he_next(he)];
+    if (a >= V || b >= V) { atomicAdd(flags + 1, 1ull); return; }
+    atomicMax(evt1 + a, he + 1); // EVT[v] = last half-edge leaving v (:1304-1308), stored +1 so 0 means none
+    const ull key = ((ull)a << 32) | b;
+    u32 slot = edge_hash(key) & mask;
+    while (true) {
+        const ull prev = atomicCAS(keys + slot, ~0ull, key);
+        if (prev == ~0ull) { vals[slot] = he; return; }
+        if (prev == key) { atomicAdd(flags, 1ull); return; } // the same directed edge twice: not edge-manifold
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void k_che_pair(const u32 *__restrict__ VT, u32 H, u32 V, const ull *__restrict__ keys, const u32 *__restrict__ vals,
+                           u32 mask, u32 *OT, u32 *border_cnt, u32 *border_he)
+{
+    const u32 he = blockIdx.x * blockDim.x + threadIdx.x;
+    if (he >= H) return;
+    const u32 a = VT[he], b = VT[he_next(he)];
+    if (a >= V || b >= V) { OT[he] = NIL; return; }
+    const ull key = ((ull)b << 32) | a;
+    u32 slot = edge_hash(key) & mask, opp = NIL;
+    while (true) {
+        const ull k = keys[slot];
+        if (k == key) { opp = vals[slot]; break; }
+        if (k == ~0ull) break;
+        slot = (slot + 1) & mask;
+    }
+    OT[he] = opp;
+    if (opp == NIL) { // border half-edge: becomes EVT of its origin (:1343-1352)
+        atomicAdd(border_cnt + a, 1u);
+        border_he[a] = he;
+    }
+}
+
+__global__ void k_che_evt(u32 V, const u32 *__restrict__ evt1, const u32 *__restrict__ border_cnt, const u32 *__restrict__ border_he,
+                          u32 *EVT, ull *flags)
+{
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const u32 bc = border_cnt[v];
+    if (bc > 1) atomicAdd(flags, 1ull); // two border half-edges at one vertex: non-manifold vertex
+    EVT[v] = bc == 1 ? border_he[v] : (evt1[v] ? evt1[v] - 1 : NIL);
+}
+
 struct TeamFlat { // plain grid-stride launch, no synchronisation
     static constexpr bool kGrid = false;
     __device__ __forceinline__ u32 cta() const { return blockIdx.x; }
@@ -554,12 +615,48 @@ void fill_stats(const ptp_mesh *m, ptp_stats_t *st, u64 launches, double ms_top,
     st->ms_total = ms_total;
 }
 
+int che_build_device(const u32 *d_vt, u64 V, u64 H, u32 *d_ot, u32 *d_evt, cudaStream_t stream, bool *manifold)
+{
+    u64 cap = 1;
+    while (cap < 2 * H) cap <<= 1;
+    ull *keys = nullptr, *flags = nullptr;
+    u32 *vals = nullptr, *evt1 = nullptr, *bcnt = nullptr, *bhe = nullptr;
+    auto cleanup = [&]() { cudaFree(keys); cudaFree(vals); cudaFree(evt1); cudaFree(bcnt); cudaFree(bhe); cudaFree(flags); };
+    auto run = [&]() -> int {
+        CK(cudaMalloc(&keys, 8 * cap));
+        CK(cudaMalloc(&vals, 4 * cap));
+        CK(cudaMalloc(&evt1, 4 * V));
+        CK(cudaMalloc(&bcnt, 4 * V));
+        CK(cudaMalloc(&bhe, 4 * V));
+        CK(cudaMalloc(&flags, 16));
+        CK(cudaMemsetAsync(keys, 0xFF, 8 * cap, stream));
+        CK(cudaMemsetAsync(evt1, 0, 4 * V, stream));
+        CK(cudaMemsetAsync(bcnt, 0, 4 * V, stream));
+        CK(cudaMemsetAsync(flags, 0, 16, stream));
+        const unsigned gh = (unsigned)((H + 255) / 256), gv = (unsigned)((V + 255) / 256);
+        k_che_insert<<<gh, 256, 0, stream>>>(d_vt, (u32)H, (u32)V, keys, vals, (u32)(cap - 1), evt1, flags);
+        k_che_pair<<<gh, 256, 0, stream>>>(d_vt, (u32)H, (u32)V, keys, vals, (u32)(cap - 1), d_ot, bcnt, bhe);
+        k_che_evt<<<gv, 256, 0, stream>>>((u32)V, evt1, bcnt, bhe, d_evt, flags);
+        CK(cudaGetLastError());
+        ull hf[2] = {0, 0};
+        CK(cudaMemcpyAsync(hf, flags, 16, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (hf[1]) return fail(PTP_ERR_INVALID, "face list references a vertex >= n_vertices");
+        *manifold = hf[0] == 0;
+        return PTP_OK;
+    };
+    const int rc = run();
+    cleanup();
+    return rc;
+}
+
 template <class R>
 int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V, u64 H, int device, ptp_mesh_t **out)
 {
     if (!out) return fail(PTP_ERR_INVALID, "out is null");
     *out = nullptr;
-    if (!GT || !VT || !OT || !EVT) return fail(PTP_ERR_INVALID, "null mesh table");
+    if (!GT || !VT) return fail(PTP_ERR_INVALID, "null mesh table");
+    if ((OT == nullptr) != (EVT == nullptr)) return fail(PTP_ERR_INVALID, "pass both OT and EVT, or neither (built on the device)");
     if (V == 0 || H == 0 || H % 3 != 0) return fail(PTP_ERR_INVALID, "need V > 0 and H = 3 * faces > 0");
     if (V >= 0x7FFFFFF0ull || H >= 0xFFFFFFF0ull) return fail(PTP_ERR_INVALID, "mesh too large for 31-bit vertex ranks");
     int ndev = 0;
@@ -605,8 +702,14 @@ int mesh_create(const R *GT, const u32 *VT, const u32 *OT, const u32 *EVT, u64 V
     } while (0)
     CKT(cudaMemcpyAsync(d_gt, GT, sizeof(R) * 3 * V, cudaMemcpyHostToDevice, m->stream));
     CKT(cudaMemcpyAsync(d_vt, VT, 4 * H, cudaMemcpyHostToDevice, m->stream));
-    CKT(cudaMemcpyAsync(d_ot, OT, 4 * H, cudaMemcpyHostToDevice, m->stream));
-    CKT(cudaMemcpyAsync(d_evt, EVT, 4 * V, cudaMemcpyHostToDevice, m->stream));
+    if (OT) {
+        CKT(cudaMemcpyAsync(d_ot, OT, 4 * H, cudaMemcpyHostToDevice, m->stream));
+        CKT(cudaMemcpyAsync(d_evt, EVT, 4 * V, cudaMemcpyHostToDevice, m->stream));
+    } else {
+        bool manifold = true;
+        if ((rc = che_build_device((const u32 *)d_vt, V, H, (u32 *)d_ot, (u32 *)d_evt, m->stream, &manifold))) { free_tmp(); return bail(rc); }
+        if (!manifold) { free_tmp(); bail(0); return fail(PTP_ERR_MESH, "face list is not an oriented edge-manifold mesh"); }
+    }
     CKT(cudaMemsetAsync(d_cnt, 0, 32, m->stream));
 
     if ((rc = dev_alloc(m, &m->GT4, sizeof(R) * 4 * V, nullptr))) { free_tmp(); return bail(rc); }
@@ -1004,6 +1107,41 @@ int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT
                         int device, ptp_mesh_t **out)
 {
     return mesh_create<double>(GT, VT, OT, EVT, V, H, device, out);
+}
+
+int ptp_che_build(const uint32_t *VT, uint64_t V, uint64_t H, uint32_t *OT, uint32_t *EVT, int device, int *manifold, double *ms)
+{
+    if (!VT || !OT || !EVT) return fail(PTP_ERR_INVALID, "null table");
+    if (V == 0 || H == 0 || H % 3 != 0 || V >= 0x7FFFFFF0ull || H >= 0x7FFFFFF0ull) return fail(PTP_ERR_INVALID, "bad sizes");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PTP_ERR_NO_DEVICE, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    u32 *d_vt = nullptr, *d_ot = nullptr, *d_evt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto run = [&]() -> int {
+        CK(cudaMalloc(&d_vt, 4 * H));
+        CK(cudaMalloc(&d_ot, 4 * H));
+        CK(cudaMalloc(&d_evt, 4 * V));
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaMemcpy(d_vt, VT, 4 * H, cudaMemcpyHostToDevice));
+        CK(cudaEventRecord(e0, nullptr));
+        bool mf = true;
+        int rc = che_build_device(d_vt, V, H, d_ot, d_evt, nullptr, &mf);
+        if (rc) return rc;
+        CK(cudaEventRecord(e1, nullptr));
+        CK(cudaMemcpy(OT, d_ot, 4 * H, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(EVT, d_evt, 4 * V, cudaMemcpyDeviceToHost));
+        if (manifold) *manifold = mf ? 1 : 0;
+        if (ms) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms = t; }
+        return PTP_OK;
+    };
+    const int rc = run();
+    cudaFree(d_vt); cudaFree(d_ot); cudaFree(d_evt);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
 }
 
 void ptp_mesh_destroy(ptp_mesh_t *m)

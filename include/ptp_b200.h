@@ -70,12 +70,22 @@ void ptp_host_free(void *p);
 /* Mesh upload. Replaces CHE::CHE(che*) + cuda_create_CHE (src/che.cpp:36-46, src/cuda/che.cu:29-48),
  * which the reference repeats on every solve; here the mesh stays resident until ptp_mesh_destroy.
  * Host tables are copied, the caller keeps ownership. Builds the per-vertex one-ring table on the
- * device (the for_star order of include/che.h:10). `device` is a CUDA ordinal. */
+ * device (the for_star order of include/che.h:10). `device` is a CUDA ordinal. OT and EVT may both be
+ * NULL: they are then built on the device from VT (see ptp_che_build). */
 int ptp_mesh_create_f32(const float *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
                         uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
 int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
                         uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
 void ptp_mesh_destroy(ptp_mesh_t *mesh);
+
+/* CHE tables from a face list, on the device. Replaces che::update_evt_ot_et (src/che.cpp:1295-1362; serial,
+ * ~22 s at 10 M vertices) for oriented edge-manifold input, for which OT / EVT equal the reference's bit for
+ * bit. VT[H] = 3 vertex ids per face; OT[H], EVT[V] are host outputs. *manifold = 0 when a directed edge occurs
+ * twice or a vertex has two border half-edges (the reference pairs such input in half-edge order; here it is
+ * reported, and ptp_mesh_create_* refuses it). *ms = device time of the build. ptp_mesh_create_* with
+ * OT == EVT == NULL runs the same build before the one-ring table. */
+int ptp_che_build(const uint32_t *VT, uint64_t n_vertices, uint64_t n_half_edges, uint32_t *OT, uint32_t *EVT,
+                  int device, int *manifold, double *ms);
 uint64_t ptp_mesh_n_vertices(const ptp_mesh_t *mesh);
 uint64_t ptp_mesh_n_half_edges(const ptp_mesh_t *mesh);
 int ptp_mesh_real_size(const ptp_mesh_t *mesh); /* 4 or 8 */

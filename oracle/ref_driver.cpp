@@ -9,6 +9,7 @@
 //
 // Reference entry points wrapped (file:line relative to /root/reference):
 //   che::che(const vertex*, n_v, const index_t*, n_f)        src/che.cpp:84-87 (init :1254-1263)
+//   che_off (OFF reader / writer)                             src/che_off.cpp:28-100
 //   che::compute_toplesets                                    src/che.cpp:546-593
 //   parallel_toplesets_propagation_cpu                        src/geodesics_ptp.cpp:122-199
 //   parallel_toplesets_propagation_coalescence_cpu            src/geodesics_ptp.cpp:40-120
@@ -18,6 +19,7 @@
 // Built twice: default (real_t = double) and with -DSINGLE_P (real_t = float).
 
 #include "geodesics_ptp.h"
+#include "che_off.h"
 
 #include <cstring>
 #include <vector>
@@ -56,6 +58,12 @@ void * ref_che_create_raw(const real_t * xyz, unsigned n_v, const unsigned * vt,
 {
 	return new che_raw(xyz, n_v, vt, ot, evt, n_f);
 }
+
+// che_off::che_off(file) — the reference's OFF reader, src/che_off.cpp:16-19,28-80
+void * ref_che_read_off(const char * path) { return new che_off(path); }
+
+// che_off::write_file, src/che_off.cpp:82-100 (appends ".off" to the name itself)
+void ref_che_write_off(void * m, const char * path_without_ext) { che_off::write_file((che *) m, path_without_ext); }
 
 void ref_che_destroy(void * m) { delete (che *) m; }
 

@@ -108,6 +108,11 @@ class Reference:
         L.ref_che_create.restype = C.c_void_p
         L.ref_che_create_raw.argtypes = [rp, C.c_uint32, u32p, u32p, u32p, C.c_uint32]
         L.ref_che_create_raw.restype = C.c_void_p
+        L.ref_che_read_off.argtypes = [C.c_char_p]
+        L.ref_che_read_off.restype = C.c_void_p
+        L.ref_che_write_off.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_che_n_vertices.argtypes = [C.c_void_p]
+        L.ref_che_n_half_edges.argtypes = [C.c_void_p]
         L.ref_che_destroy.argtypes = [C.c_void_p]
         L.ref_che_tables.argtypes = [C.c_void_p, rp, u32p, u32p, u32p]
         L.ref_compute_toplesets.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_uint32, u32p, u32p, u32p]
@@ -125,6 +130,11 @@ class Reference:
         VT = _u32(faces).reshape(-1)
         return RefChe(self, self.L.ref_che_create(_p(xyz, self.ct), xyz.shape[0], _p(VT), VT.size // 3), xyz.shape[0], VT.size)
 
+    def read_off(self, path):
+        """the reference's own OFF reader (che_off)"""
+        h = self.L.ref_che_read_off(str(path).encode())
+        return RefChe(self, h, self.L.ref_che_n_vertices(h), self.L.ref_che_n_half_edges(h))
+
     def che_raw(self, mesh):
         """inject prebuilt tables (skips the serial construction; for large meshes)"""
         GT = np.ascontiguousarray(mesh.GT, dtype=self.dt)
@@ -140,6 +150,9 @@ class RefChe:
         if self.h:
             self.ref.L.ref_che_destroy(self.h)
             self.h = None
+
+    def write_off(self, path_without_ext):
+        self.ref.L.ref_che_write_off(self.h, str(path_without_ext).encode())
 
     def tables(self):
         GT = np.empty((self.n_v, 3), dtype=self.ref.dt)

@@ -199,3 +199,90 @@ def test_errors_are_reported(gpu):
     bad.OT[:] = 5  # every walk cycles without returning to its start
     with pytest.raises(api.PtpError):
         api.DeviceMesh(bad, gpu)
+
+
+# ---------------------------------------------------------------- CHE construction on the device
+
+@pytest.mark.parametrize("name", ["grid", "torus", "ico", "hole", "fan_open"])
+def test_che_build_device_matches_reference_tables(name, oracle, gpu):
+    from cases import fan_mesh
+    m = {"grid": mg.grid(23, 31), "torus": mg.torus(30, 12), "ico": mg.icosphere(9),
+         "hole": mg.punch_hole(mg.grid(21), 10 * 21 + 10, 2), "fan_open": fan_mesh(11, False)}[name]
+    OT, EVT, manifold, ms = api.che_build(m.VT, m.n_vertices, gpu)
+    OTo, EVTo, _ = oracle.che_build(m.n_vertices, m.VT)   # restatement of che::update_evt_ot_et, pinned to the reference
+    assert manifold and ms > 0
+    assert np.array_equal(OT, OTo) and np.array_equal(EVT, EVTo)
+
+
+def test_che_build_device_flags_non_manifold(gpu):
+    faces = np.array([0, 1, 2, 0, 1, 3, 0, 1, 4], dtype=np.uint32)  # directed edge 0->1 three times
+    _, _, manifold, _ = api.che_build(faces, 5, gpu)
+    assert not manifold
+    with pytest.raises(api.PtpError):
+        api.DeviceMesh(api.FaceMesh(np.zeros((5, 3)), faces), gpu)
+    bowtie = np.array([0, 1, 2, 0, 3, 4], dtype=np.uint32)  # two border fans meeting at vertex 0
+    _, _, manifold, _ = api.che_build(bowtie, 5, gpu)
+    assert not manifold
+
+
+def test_mesh_from_faces_equals_mesh_from_tables(oracle, gpu):
+    m = mg.icosphere(11, 4e-3, seed=8).astype(np.float32)
+    with api.DeviceMesh(m, gpu) as a, api.DeviceMesh(api.FaceMesh(m.GT, m.VT), gpu) as b:
+        da, _, sa = a.geodesics([3, 99], want_sorted=True)
+        db, _, sb = b.geodesics([3, 99], want_sorted=True)
+    assert np.array_equal(da, db) and np.array_equal(sa, sb)
+
+
+# ---------------------------------------------------------------- BASELINE configs at their stated sizes
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_config_c1_grid_through_off(dtype, oracle, gpu, tmp_path):
+    """configs[0]: 317x317 grid (100 489 vertices) written to / read from OFF, source = centre vertex."""
+    from gproshan_b200.off_io import read_off, write_off
+    g = mg.grid(317)
+    write_off(tmp_path / "grid317.off", g.GT, g.VT)
+    xyz, faces = read_off(tmp_path / "grid317.off", dtype=dtype)
+    src = [158 * 317 + 158]
+    with api.DeviceMesh(api.FaceMesh(xyz, faces), gpu) as dm:
+        got, _, srt = dm.geodesics(src, want_sorted=True)
+        stats = dict(dm.last_stats)
+    m = g.astype(dtype)
+    t0, s0, l0 = oracle.compute_toplesets(m, src)
+    want, _, st = oracle.ptp_cpu(m, src, l0, s0)
+    assert np.array_equal(srt, s0[:l0[-1]])
+    assert_dist_parity(got, want, dtype, "C1")
+    assert stats["vertex_updates"] == st["vertex_updates"]
+    # sanity (not parity): on the flat grid PTP is within a few % of the Euclidean distance
+    eu = np.linalg.norm(g.GT - g.GT[src[0]], axis=1)
+    assert np.abs(got - eu).max() < 0.05
+
+
+def test_config_c2_icosphere_1m_float(oracle, gpu):
+    """configs[1]: 998 562-vertex icosphere, float, single source."""
+    m = mg.icosphere(316, dtype=np.float32)
+    assert m.n_vertices == 998562
+    with api.DeviceMesh(m, gpu) as dm:
+        got, _, srt = dm.geodesics([0], want_sorted=True)
+    t0, s0, l0 = oracle.compute_toplesets(m, [0])
+    want, _, _ = oracle.ptp_cpu(m, [0], l0, s0)
+    assert np.array_equal(srt, s0[:l0[-1]])
+    assert_dist_parity(got, want, np.float32, "C2")
+    gc = np.arccos(np.clip(m.GT.astype(np.float64) @ m.GT[0].astype(np.float64), -1, 1))
+    assert np.abs(got - gc).max() < 0.08  # sanity: great-circle distance on the unit sphere
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_three_device_paths_agree_at_scale(dtype, gpu):
+    """Size-independent property, no oracle needed: the fused two-team kernel (ptp_geodesics), the stand-alone
+    sweep fed with toplesets from ptp_toplesets (ptp_solve) and the one-CTA-per-solve kernel (ptp_solve_batched)
+    are three different schedules of the same arithmetic and must agree bit for bit; so must repeated runs."""
+    m = mg.icosphere(400, noise_sigma=0.2 * mg.mean_edge_icosphere(400), seed=12345, dtype=dtype)  # 1.6 M vertices
+    src = [123456]
+    with api.DeviceMesh(m, gpu) as dm:
+        a, _, _ = dm.geodesics(src)
+        a2, _, _ = dm.geodesics(src)
+        top, srt, lim = dm.compute_toplesets(src)
+        b, _ = dm.solve(src, lim, srt)
+        c = dm.solve_batched(np.array(src, dtype=np.uint32))[0]
+    assert np.array_equal(a, a2) and np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.isfinite(a).all() and a[src[0]] == 0 and (top != NIL).all()

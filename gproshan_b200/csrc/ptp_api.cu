@@ -225,6 +225,22 @@ __global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> 
     bfs_run<R, TeamGrid, false>(t, m, w, sources, S, kcap, sent);
 }
 
+// DEBUG (PTP_FUSED=2): the two halves of the fused kernel as two launches, to time the streamed sweep alone
+template <class R>
+__global__ void __launch_bounds__(FUSED_BLOCK, 2) k_dbg_producer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 sent, ull *bar)
+{
+    TeamGrid t{bar, 0, 0, gridDim.x};
+    bfs_run<R, TeamGrid, true>(t, m, w, sources, S, NIL, sent);
+}
+template <class R>
+__global__ void __launch_bounds__(FUSED_BLOCK, 2)
+k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 sent, ull *bar)
+{
+    TeamGrid t{bar, 0, 0, gridDim.x};
+    const u32 d = ptp_run<R, TeamGrid, false, 8, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+    scatter_run<R, TeamGrid, false>(t, m, w, d, dist_out, nullptr, 0u);
+}
+
 template <class R> __global__ void k_inv_init(MeshView<R> m, Work<R> w)
 {
     const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -832,6 +848,25 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     int rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
+    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 1; }();
+    if (dbg == 2 && !cl) {
+        MeshView<R> mv = mesh_view<R>(m);
+        Work<R> w = work_view<R>(m);
+        w.cl[0] = w.cl[1] = nullptr;
+        const u32 *src = (const u32 *)m->w_src;
+        R *out = (R *)m->w_out;
+        ull *bar = (ull *)m->w_bar;
+        u32 sent = (u32)(m->V + m->ws_scap);
+        void *a1[] = {&mv, &w, &src, &S, &sent, &bar};
+        void *a2[] = {&mv, &w, &src, &S, &out, &sent, &bar};
+        CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_dbg_producer<R>, dim3(m->num_sms), dim3(FUSED_BLOCK), a1, 0, m->stream));
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_dbg_consumer<R>, dim3(m->num_sms), dim3(FUSED_BLOCK), a2, 0, m->stream));
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        return PTP_OK;
+    }
     if (use_fused()) {
         if ((rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
         CK(cudaEventRecord(m->ev[1], m->stream));
@@ -865,11 +900,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
     }
     if ((rc = fetch_ctrl(m))) return rc;
-    if (use_fused()) {
+    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
+        fill_stats(m, st, 2, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    else if (use_fused()) {
         // one launch: the producer / consumer split comes from %globaltimer stamps written by the kernel
         const ull *c = (const ull *)m->h_ctrl;
         const double t_bfs = c[C_TBFS] > c[C_TSTART] ? (c[C_TBFS] - c[C_TSTART]) * 1e-6 : 0.0;
         const double t_all = ev_ms(m->ev[0], m->ev[2]);
+        if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] producer polls by the sweep team: %llu\n", c[C_ARGMAX]);
         fill_stats(m, st, 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
     } else
         fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));

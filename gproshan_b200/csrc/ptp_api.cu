@@ -45,6 +45,9 @@ template <class R> struct BatchCfg;                    // threads per CTA, one-s
 template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
 template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; };
 constexpr int FLAT_BLOCK = 256;
+#ifndef PTP_GRID_MAP
+#define PTP_GRID_MAP 4 // lanes per vertex in the whole-GPU sweep: 8 (one triangle per lane) or 4 (two per lane)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 2)
 k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 sent, ull *bar)
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
-    const u32 d = ptp_run<R, TeamGrid, false, 8, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+    const u32 d = ptp_run<R, TeamGrid, false, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, false>(t, m, w, d, dist_out, nullptr, 0u);
 }
 
@@ -267,7 +270,7 @@ k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
     const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-    const u32 d = ptp_run<R, TeamGrid, CL, 8, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
 }
 
@@ -285,7 +288,7 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
     } else {
         TeamGrid t{bar + 64, 0, nb, gridDim.x - nb};
-        const u32 d = ptp_run<R, TeamGrid, CL, 8, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
         scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
         if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
     }

@@ -3,13 +3,15 @@ import numpy as np
 from gproshan_b200 import api, meshgen as mg
 from oracle_lib import Oracle
 o=Oracle()
-m=mg.grid(41).astype(np.float32); src=[20*41+20]
-t,s,l=o.compute_toplesets(m,src); want,_,st=o.ptp_cpu(m,src,l,s)
+m = mg.icosphere(400, noise_sigma=0.2 * mg.mean_edge_icosphere(400), seed=12345, dtype=np.float32)
+src=[123456]
+t,s,l=o.compute_toplesets(m,src); want,_,st=o.ptp_cpu(m,src,l,s); print(st)
 with api.DeviceMesh(m,0) as dm:
-    got,_,srt=dm.geodesics(src,want_sorted=True); print(dm.last_stats, st)
-print('sorted equal', np.array_equal(srt,s[:l[-1]]))
-bad=np.nonzero(got!=want)[0]; print('nbad',bad.size, 'of', got.size)
-inv=np.empty(m.n_vertices,int); inv[s[:l[-1]]]=np.arange(l[-1])
-lev=t
-print('bad levels hist', np.bincount(lev[bad])[:45])
-for v in bad[:10]: print(v, 'lvl',lev[v],'rank',inv[v], got[v], want[v])
+    a,_,_=dm.geodesics(src); sa=dict(dm.last_stats)
+    top,srt,lim=dm.compute_toplesets(src)
+    b,_=dm.solve(src,lim,srt); sb=dict(dm.last_stats)
+    c=dm.solve_batched(np.array(src,dtype=np.uint32))[0]; sc=dict(dm.last_stats)
+for name,x,stt in (('fused',a,sa),('solve',b,sb),('batched',c,sc)):
+    bad=np.nonzero(x!=want)[0]
+    print(name,'nbad',bad.size,'iters',stt['iterations'],'upd',stt['vertex_updates'],'relax',stt['relaxations'], 'maxrel', (np.abs(x-want)/np.maximum(want,1e-30)).max())
+    if bad.size: print('  levels of bad', np.unique(t[bad])[:20], 'first', bad[:5], x[bad[:5]], want[bad[:5]])

@@ -37,6 +37,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+    (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -279,10 +289,13 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(host_np.nbytes), "steps": e2e_steps, "checksum": checksum},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_batched<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_batched_f32_c5_128"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[4], "vertex_updates_per_launch": updates,
+                     "achieved_counting_executed_relaxations_only": st["relaxations"] * BYTES_PER_UPDATE[4] / (kernel_ms / 1e3) / 1e9,
                      "relaxations_per_launch": st["relaxations"], "kernel_ms": kernel_ms,
-                     "note": "rank 0's kernel; includes BFS + layout + sweep of every source in the launch"},
+                     "note": "rank 0's kernel; includes BFS + layout + sweep of every source in the launch. vertex_updates = the "
+                             "reference schedule's window sizes (skipped relaxations included); the kernel is FP32-issue "
+                             "bound, not HBM bound (profiles/)"},
         "clocks": clocks,
     }
 
@@ -320,15 +333,20 @@ def run_single(args, api, torch, peak, peak_src):
     st = dm.last_stats
     ms = statistics.median(dev_ms)
     sweep_ms = statistics.median(sol_ms)
-    achieved = st["vertex_updates"] * BYTES_PER_UPDATE[8] / (sweep_ms / 1e3) / 1e9
+    achieved = st["vertex_updates"] * BYTES_PER_UPDATE[8] / (ms / 1e3) / 1e9
+    t = time.perf_counter()
+    _, _, manifold, che_ms = api.che_build(mesh.VT, V, torch.cuda.current_device())
+    che_wall = time.perf_counter() - t
     res = {
-        "workload": wl, "ms_per_solve": ms, "ms_toplesets_and_layout": statistics.median(top_ms), "ms_sweep": sweep_ms,
+        "workload": wl, "ms_per_solve": ms, "ms_bfs_team": statistics.median(top_ms), "ms_until_sweep_team_done": sweep_ms,
+        "che_build": {"device_ms": che_ms, "ms_with_h2d_d2h": che_wall * 1e3, "manifold": manifold,
+                      "note": "OT/EVT from the face list on the device (reference: che::update_evt_ot_et, serial)"},
         "vertex_updates": st["vertex_updates"], "relaxations": st["relaxations"], "iterations": st["iterations"], "levels": st["n_levels"],
         "max_window": st["max_window"], "vertex_updates_per_s": st["vertex_updates"] / (ms / 1e3),
         "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
         "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],
-        "roofline": {"bound": "hbm", "kernel": "k_solve_grid<double>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k_geodesics_fused<double> (BFS team + sweep team, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_geodesics_fused_f64_c3"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[8],
                      "note": "latency-bound by construction: ~#toplesets dependent iterations (SURVEY.md §0.4)"},
     }

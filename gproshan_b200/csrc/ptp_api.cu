@@ -315,10 +315,11 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         const u32 *src = sources + o0;
         if (threadIdx.x == 0) { w.ctrl[C_OVFALLOC] = 0; w.ctrl[C_RELAXED] = 0; }
         const ull t0 = global_timer();
-        bfs_run<R, TeamCta, false>(t, m, w, src, S, NIL, sent);
+        bfs_run_cta<R>(m, w, src, S);
         const ull t1 = global_timer();
         const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-        layout_run<R, TeamCta>(t, m, w, p, sent);
+        layout_rows_thread<R>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
+        __syncthreads();
         const ull t2 = global_timer();
         const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
@@ -1053,6 +1054,9 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         st->gpu_launches = launches;
         // CTA-time spent in BFS + layout, and in the sweep, averaged over the CTAs that ran (device timers)
         const double ctas = (double)std::min<u64>(m->bt_slots, B);
+        if (getenv("PTP_DEBUG"))
+            fprintf(stderr, "[ptp] batched mean per-CTA ms: bfs %.1f layout %.1f sweep+scatter %.1f\n", tot[7] * 1e-6 / ctas,
+                    tot[8] * 1e-6 / ctas, tot[9] * 1e-6 / ctas);
         st->ms_toplesets = (double)(tot[7] + tot[8]) * 1e-6 / ctas;
         st->ms_solve = (double)tot[9] * 1e-6 / ctas;
         st->ms_total = ev_ms(m->ev[0], m->ev[1]);

@@ -214,7 +214,6 @@ __global__ void k_che_evt(u32 V, const u32 *__restrict__ evt1, const u32 *__rest
 }
 
 struct TeamFlat { // plain grid-stride launch, no synchronisation
-    static constexpr bool kGrid = false;
     __device__ __forceinline__ u32 cta() const { return blockIdx.x; }
     __device__ __forceinline__ u32 nctas() const { return gridDim.x; }
     __device__ __forceinline__ u32 sync(u32 = 0) { return 0; }

@@ -286,3 +286,25 @@ def test_three_device_paths_agree_at_scale(dtype, gpu):
         c = dm.solve_batched(np.array(src, dtype=np.uint32))[0]
     assert np.array_equal(a, a2) and np.array_equal(a, b) and np.array_equal(a, c)
     assert np.isfinite(a).all() and a[src[0]] == 0 and (top != NIL).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_config_c4_shape_multi_source_voronoi(dtype, oracle, gpu):
+    """configs[3] at 1/9 of its size (same aspect 3780:1323, R=1, r=0.35): 64 sources `mt19937(7)() % V`, clusters on.
+    Distances bit-equal, Voronoi clusters equal, every reached vertex labelled 1..64."""
+    m = mg.torus(1260, 441).astype(dtype)
+    src = mg.random_sources(7, 64, m.n_vertices)
+    t0, s0, l0 = oracle.compute_toplesets(m, src)
+    want, want_cl, st = oracle.ptp_cpu(m, src, l0, s0, clusters=True)
+    with api.DeviceMesh(m, gpu) as dm:
+        got, cl, srt = dm.geodesics(src, clusters=True, want_sorted=True)
+        stats = dict(dm.last_stats)
+        g2 = api.geodesics(dm, src, api.geodesics.PTP_GPU, cluster=True)
+    assert np.array_equal(srt, s0[:l0[-1]])
+    assert_dist_parity(got, want, dtype, "C4-shape")
+    assert np.array_equal(cl, want_cl) and cl.min() >= 1 and cl.max() <= 64
+    assert stats["iterations"] == st["iterations"] and stats["vertex_updates"] == st["vertex_updates"]
+    assert stats["relaxations"] < stats["vertex_updates"]
+    assert np.array_equal(g2.dist, got) and np.array_equal(g2.clusters, cl)
+    # each source is its own nearest source
+    assert np.array_equal(cl[src], 1 + np.array([np.nonzero(src == s)[0].max() for s in src]))

@@ -36,7 +36,7 @@ SYMBOLS = [
     "ptp_mesh_n_half_edges", "ptp_mesh_real_size", "ptp_mesh_device", "ptp_mesh_device_bytes",
     "ptp_toplesets", "ptp_solve_f32", "ptp_solve_f64", "ptp_geodesics_f32", "ptp_geodesics_f64",
     "ptp_solve_batched_f32", "ptp_solve_batched_f64",
-    "ptp_farthest_point_sampling_f32", "ptp_farthest_point_sampling_f64",
+    "ptp_farthest_point_sampling_f32", "ptp_farthest_point_sampling_f64", "ptp_debug_barrier_ns",
 ]
 
 _LIB = None
@@ -72,6 +72,8 @@ def lib():
         f = getattr(L, f"ptp_farthest_point_sampling_{suf}")
         f.argtypes = [vp, u32p, C.c_uint32, C.c_uint32, ct, u32p, rp, sp]
     L.ptp_che_build.argtypes = [u32p, C.c_uint64, C.c_uint64, u32p, u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.ptp_debug_barrier_ns.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ptp_debug_barrier_ns.restype = C.c_double
     L.ptp_mesh_destroy.argtypes = [vp]
     L.ptp_mesh_destroy.restype = None
     for n in ("ptp_mesh_n_vertices", "ptp_mesh_n_half_edges", "ptp_mesh_device_bytes"):

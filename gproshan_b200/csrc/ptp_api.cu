@@ -243,6 +243,15 @@ k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out,
     scatter_run<R, TeamGrid, false>(t, m, w, d, dist_out, nullptr, 0u);
 }
 
+// DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
+__global__ void k_dbg_barriers(ull *bar, u32 n, u32 *sink)
+{
+    TeamGrid t{bar, 0, 0, gridDim.x};
+    u32 acc = 0;
+    for (u32 i = 0; i < n; i++) acc += t.sync(i & 1u);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *sink = acc;
+}
+
 template <class R> __global__ void k_inv_init(MeshView<R> m, Work<R> w)
 {
     const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,11 +274,13 @@ template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshVi
 
 template <class R, bool CL>
 __global__ void __launch_bounds__(SOLVE_BLOCK)
-k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar)
+k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged)
 {
+    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     TeamGrid t{bar, 0, 0, gridDim.x};
     const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
+                                                               staged ? ptp_dyn_smem : nullptr);
     scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
 }
 
@@ -278,8 +289,10 @@ k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u
 // (~#levels dependent iterations) overlap instead of adding up.
 template <class R, bool CL>
 __global__ void __launch_bounds__(FUSED_BLOCK, 2)
-k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb)
+k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb,
+                  u32 staged)
 {
+    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     if (blockIdx.x < nb) {
         TeamGrid t{bar, 0, 0, nb};
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
@@ -287,7 +300,8 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
     } else {
         TeamGrid t{bar + 64, 0, nb, gridDim.x - nb};
-        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
+                                                                  staged ? ptp_dyn_smem : nullptr);
         scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
         if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
     }
@@ -563,6 +577,12 @@ template <class R> int launch_layout(ptp_mesh *m)
     return PTP_OK;
 }
 
+bool use_staging()
+{
+    static int v = [] { const char *e = getenv("PTP_STAGE"); return e ? atoi(e) : 1; }();
+    return v != 0 && PTP_GRID_MAP == 4;
+}
+
 template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     MeshView<R> mv = mesh_view<R>(m);
@@ -576,9 +596,12 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     u32 *clo = (u32 *)m->w_clout;
     ull *bar = (ull *)m->w_bar;
     u32 sent = (u32)(m->V + m->ws_scap);
-    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar};
+    u32 staged = use_staging() ? 1u : 0u;
+    const size_t smem = staged ? SOLVE_BLOCK * Stage4<R>::bytes_per_thread() : 0;
+    if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged};
     CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_BLOCK), args, 0, m->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_BLOCK), args, smem, m->stream));
     return PTP_OK;
 }
 
@@ -602,8 +625,20 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     Work<R> w = work_view<R>(m);
     if (!cl) w.cl[0] = w.cl[1] = nullptr;
     void *fn = cl ? (void *)k_geodesics_fused<R, true> : (void *)k_geodesics_fused<R, false>;
+    // Staging the window in shared memory pays in the stand-alone sweep (1 CTA per SM); with two CTAs per SM it
+    // takes 160 KB of the SM's 228 KB L1/shared array away from both teams and measured slower (C3: 32.8 vs
+    // 29.6 ms), so the fused kernel runs unstaged unless PTP_STAGE=2.
+    static const bool stage_fused = [] { const char *e = getenv("PTP_STAGE"); return e && atoi(e) == 2; }();
+    u32 staged = (stage_fused && PTP_GRID_MAP == 4) ? 1u : 0u;
+    size_t smem = staged ? FUSED_BLOCK * Stage4<R>::bytes_per_thread() : 0;
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FUSED_BLOCK, 0));
+    if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FUSED_BLOCK, smem));
+    if (per_sm < 2 && staged) { // not enough shared memory for two staged CTAs per SM: run unstaged
+        staged = 0;
+        smem = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FUSED_BLOCK, 0));
+    }
     if (per_sm < 2) return fail(PTP_ERR_CUDA, "fused kernel needs two resident CTAs per SM");
     const int grid = 2 * m->num_sms;
     const u32 *src = (const u32 *)m->w_src;
@@ -612,9 +647,9 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     ull *bar = (ull *)m->w_bar;
     u32 sent = (u32)(m->V + m->ws_scap);
     u32 nb = (u32)bfs_ctas(m);
-    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb};
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb, &staged};
     CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
-    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FUSED_BLOCK), args, 0, m->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FUSED_BLOCK), args, smem, m->stream));
     return PTP_OK;
 }
 
@@ -1186,6 +1221,32 @@ int ptp_che_build(const uint32_t *VT, uint64_t V, uint64_t H, uint32_t *OT, uint
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;
+}
+
+// measurement helper (not part of the reference interface): nanoseconds per grid barrier of `ctas` CTAs x `block` threads
+double ptp_debug_barrier_ns(int ctas, int block, int n)
+{
+    ull *bar = nullptr;
+    u32 *sink = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaMalloc(&bar, 1024) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) return -1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    u32 nn = (u32)n;
+    void *args[] = {&bar, &nn, &sink};
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaMemset(bar, 0, 1024);
+        cudaEventRecord(e0);
+        if (cudaLaunchCooperativeKernel((void *)k_dbg_barriers, dim3(ctas), dim3(block), args, 0, nullptr) != cudaSuccess) { best = -1; break; }
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = ms < best ? ms : best;
+    }
+    cudaFree(bar); cudaFree(sink); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best < 0 ? -1 : (double)best * 1e6 / n;
 }
 
 void ptp_mesh_destroy(ptp_mesh_t *m)

@@ -151,6 +151,10 @@ int ptp_farthest_point_sampling_f32(ptp_mesh_t *mesh, uint32_t *samples, uint32_
 int ptp_farthest_point_sampling_f64(ptp_mesh_t *mesh, uint32_t *samples, uint32_t n_initial, uint32_t n_total,
                                     double radio, uint32_t *n_out, double *max_dist, ptp_stats_t *stats);
 
+/* Measurement helper, not part of the reference interface: nanoseconds per grid barrier (the fused
+ * arrive + reduce + poll barrier of the single-solve kernels) for `ctas` CTAs of `block` threads; < 0 on error. */
+double ptp_debug_barrier_ns(int ctas, int block, int n);
+
 #ifdef __cplusplus
 }
 #endif

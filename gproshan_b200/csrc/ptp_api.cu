@@ -39,6 +39,10 @@ int fail(int code, const std::string &msg)
     } while (0)
 
 constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
+#ifndef PTP_MERGED_BLOCK
+#define PTP_MERGED_BLOCK 512
+#endif
+constexpr int MERGED_BLOCK = PTP_MERGED_BLOCK; // merged single-solve kernel: 1 CTA per SM
 constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
 constexpr int SOLVE_BLOCK = 1024;  // threads per CTA, cooperative sweep kernel (one pass per iteration on C3-size windows)
 template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
@@ -225,6 +229,20 @@ __global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> 
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
     bfs_run<R, TeamGrid, false>(t, m, w, sources, S, kcap, sent);
+}
+
+// Single solve, one cooperative launch, ONE team running the BFS and the sweep in lock step (PTP_FUSED=3).
+template <class R, bool CL>
+__global__ void __launch_bounds__(MERGED_BLOCK)
+k_geodesics_merged(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged)
+{
+    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
+    TeamGrid t{bar, 0, 0, gridDim.x};
+    BfsHook<R, TeamGrid> hook(t, m, w, sent);
+    hook.b.init(sources, S);
+    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false, BfsHook<R, TeamGrid>>(
+        t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0, staged ? ptp_dyn_smem : nullptr, &hook);
+    scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
 }
 
 // DEBUG (PTP_FUSED=2): the two halves of the fused kernel as two launches, to time the streamed sweep alone
@@ -905,6 +923,26 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
         CK(cudaEventRecord(m->ev[2], m->stream));
         return PTP_OK;
     }
+    if (dbg == 3) {
+        MeshView<R> mv = mesh_view<R>(m);
+        Work<R> w = work_view<R>(m);
+        if (!cl) w.cl[0] = w.cl[1] = nullptr;
+        void *fn = cl ? (void *)k_geodesics_merged<R, true> : (void *)k_geodesics_merged<R, false>;
+        const u32 *src = (const u32 *)m->w_src;
+        R *out = (R *)m->w_out;
+        u32 *clo = (u32 *)m->w_clout;
+        ull *bar = (ull *)m->w_bar;
+        u32 sent = (u32)(m->V + m->ws_scap);
+        u32 staged = use_staging() ? 1u : 0u;
+        const size_t smem = staged ? MERGED_BLOCK * Stage4<R>::bytes_per_thread() : 0;
+        if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged};
+        CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+        CK(cudaLaunchCooperativeKernel(fn, dim3(m->num_sms), dim3(MERGED_BLOCK), args, smem, m->stream));
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        return PTP_OK;
+    }
     if (use_fused()) {
         if ((rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
         CK(cudaEventRecord(m->ev[1], m->stream));
@@ -938,7 +976,9 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
     }
     if ((rc = fetch_ctrl(m))) return rc;
-    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
+    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 3)
+        fill_stats(m, st, 1, 0.0, ev_ms(m->ev[0], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    else if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
         fill_stats(m, st, 2, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     else if (use_fused()) {
         // one launch: the producer / consumer split comes from %globaltimer stamps written by the kernel

@@ -40,7 +40,7 @@ int fail(int code, const std::string &msg)
 
 constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
 #ifndef PTP_MERGED_BLOCK
-#define PTP_MERGED_BLOCK 512
+#define PTP_MERGED_BLOCK 1024
 #endif
 constexpr int MERGED_BLOCK = PTP_MERGED_BLOCK; // merged single-solve kernel: 1 CTA per SM
 constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
@@ -233,12 +233,13 @@ __global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> 
 
 // Single solve, one cooperative launch, ONE team running the BFS and the sweep in lock step (PTP_FUSED=3).
 template <class R, bool CL>
-__global__ void __launch_bounds__(MERGED_BLOCK)
-k_geodesics_merged(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged)
+__global__ void __launch_bounds__(MERGED_BLOCK, 1)
+k_geodesics_merged(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged,
+                   u32 bfs_threads)
 {
     extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     TeamGrid t{bar, 0, 0, gridDim.x};
-    BfsHook<R, TeamGrid> hook(t, m, w, sent);
+    BfsHook<R, TeamGrid> hook(t, m, w, sent, bfs_threads);
     hook.b.init(sources, S);
     const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false, BfsHook<R, TeamGrid>>(
         t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0, staged ? ptp_dyn_smem : nullptr, &hook);
@@ -936,7 +937,9 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
         u32 staged = use_staging() ? 1u : 0u;
         const size_t smem = staged ? MERGED_BLOCK * Stage4<R>::bytes_per_thread() : 0;
         if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged};
+        static const u32 bfs_warps = [] { const char *e = getenv("PTP_BFS_WARPS"); return e ? (u32)atoi(e) : 8u; }();
+        u32 bfs_threads = std::min<u32>(bfs_warps * 32u, MERGED_BLOCK - 64u); // 0 = no warp roles
+        void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged, &bfs_threads};
         CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
         CK(cudaLaunchCooperativeKernel(fn, dim3(m->num_sms), dim3(MERGED_BLOCK), args, smem, m->stream));
         CK(cudaEventRecord(m->ev[1], m->stream));

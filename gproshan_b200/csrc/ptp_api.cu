@@ -330,18 +330,23 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
 template <class R>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
 k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
-          ull *queue, ull *totals)
+          ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */)
 {
     __shared__ u32 s_b;
     __shared__ u32 s_wl[2];
     TeamCta t;
     const Work<R> w = works[blockIdx.x];
+    HelpDesc *help = descs ? descs + blockIdx.x : nullptr;
     while (true) {
         if (threadIdx.x == 0) s_b = (u32)atomicAdd(queue, 1ull);
         __syncthreads();
         const u32 b = s_b;
         __syncthreads();
-        if (b >= B) break;
+        if (b >= B) {
+            // no solve left for this CTA: lend its threads to the relax passes of the solves still running
+            if (descs) help_loop<R>(works, descs, gridDim.x, counters, counters + 1, B);
+            break;
+        }
         const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
         const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
         const u32 *src = sources + o0;
@@ -353,7 +358,8 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         layout_rows_thread<R>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
         __syncthreads();
         const ull t2 = global_timer();
-        const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0);
+        const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr,
+                                                          (NoHook *)nullptr, help, counters);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -361,6 +367,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
             atomicAdd(totals + 6, t1 - t0); // per-phase device time summed over solves (ns)
             atomicAdd(totals + 7, t2 - t1);
             atomicAdd(totals + 8, t3 - t2);
+            if (descs) { __threadfence(); atomicAdd(counters + 1, 1u); }
             atomicAdd(totals + 0, w.ctrl[C_ITER]);
             atomicAdd(totals + 1, w.ctrl[C_UPDATES]);
             atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
@@ -441,7 +448,7 @@ struct ptp_mesh {
     u32 bt_slots = 0;
     u64 bt_scap = 0;
     std::vector<void *> bt_allocs;
-    void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr;
+    void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr, *bt_help = nullptr;
     u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
 };
 
@@ -1050,6 +1057,7 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
         }
         if ((rc = dev_alloc(m, &m->bt_works, sizeof(Work<R>) * slots, &tr))) return rc;
         if ((rc = dev_alloc(m, &m->bt_queue, 128, &tr))) return rc;
+        if ((rc = dev_alloc(m, &m->bt_help, sizeof(HelpDesc) * slots + 64, &tr))) return rc;
         CK(cudaMemcpy(m->bt_works, hw.data(), sizeof(Work<R>) * slots, cudaMemcpyHostToDevice));
         m->bt_slots = slots;
         m->bt_scap = scap;
@@ -1108,10 +1116,15 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         const u32 nb = (u32)std::min<u64>(chunk, B - first);
         R *dst = on_device ? rows + first * m->V : (R *)m->bt_rows;
         CK(cudaMemsetAsync(queue, 0, 8, stream));
-        const u32 grid = std::min<u32>(m->bt_slots, nb);
+        // elastic mode (PTP_ELASTIC=0 disables): every slot's CTA is launched; those beyond the batch help from the start
+        static const bool elastic = [] { const char *e = getenv("PTP_ELASTIC"); return e ? atoi(e) != 0 : true; }();
+        HelpDesc *descs = elastic ? (HelpDesc *)m->bt_help : nullptr;
+        u32 *counters = (u32 *)((char *)m->bt_help + sizeof(HelpDesc) * m->bt_slots);
+        if (elastic) CK(cudaMemsetAsync(m->bt_help, 0, sizeof(HelpDesc) * m->bt_slots + 64, stream));
+        const u32 grid = elastic ? m->bt_slots : std::min<u32>(m->bt_slots, nb);
         k_batched<R><<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
                                                         offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
-                                                        (u32)(m->V + m->bt_scap), queue, queue + 1);
+                                                        (u32)(m->V + m->bt_scap), queue, queue + 1, descs, counters);
         CK(cudaGetLastError());
         launches++;
         if (!on_device)

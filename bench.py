@@ -158,6 +158,24 @@ def cpu_sources_per_s(mesh, srcs, budget_s, max_n):
     return kind, n, dt
 
 
+def reference_gpu_leg(workload, quick, sources, coalescence):
+    """Second baseline: the reference's own CUDA PTP (unmodified, sm_100a build in oracle/_ref) on this GPU, in a
+    process of its own (it calls cudaDeviceReset()). See tools/ref_gpu_bench.py for what is timed."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_gpu_bench.py"), "--workload", workload, "--sources", str(sources)]
+    if quick:
+        cmd.append("--quick")
+    if coalescence:
+        cmd.append("--coalescence")
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": f"exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # the baseline must never take the bench line down
+        return {"unavailable": repr(e)}
+
+
 # ------------------------------------------------------------------------------------------------ arms
 
 def run_reference(args, rank, world):
@@ -306,6 +324,11 @@ def run_b200(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": n / dt, "unit": "sources/s", "cores": os.cpu_count(), "kind": kind,
                                 "sample": f"{n} of the {per_gpu} sources of this workload, {dt:.1f}s, OpenMP on all host threads"}
     dm.close()
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
+        torch.cuda.synchronize()
+        if "single_source" in line:
+            line["single_source"]["reference_gpu"] = reference_gpu_leg("c3", args.quick, 1, True)
+        line["reference_gpu"] = reference_gpu_leg("c5", args.quick, 3, False)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
@@ -374,6 +397,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=128)
     ap.add_argument("--quick", action="store_true", help="small meshes (smoke / CI)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own CUDA PTP (second baseline)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-sources-per-step", type=int, default=1)
     ap.add_argument("--ref-budget-s", type=float, default=150.0)

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptp_b200.so")
+# PTP_B200_LIB: development hook for A/B runs of differently compiled builds of the same library
+LIB_PATH = os.environ.get("PTP_B200_LIB") or os.path.join(_HERE, "libptp_b200.so")
 
 PTP_OK = 0
 PTP_NIL = 0xFFFFFFFF

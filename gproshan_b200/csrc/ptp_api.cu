@@ -44,6 +44,10 @@ constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
 #endif
 constexpr int MERGED_BLOCK = PTP_MERGED_BLOCK; // merged single-solve kernel: 1 CTA per SM
 constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
+#ifndef PTP_CLUSTER_BLOCK
+#define PTP_CLUSTER_BLOCK 768 // measured on C3 (f64): 768 threads / 80 registers 27.9 ms, 1024 / 64 29.8, 512 / 128 28.0
+#endif
+constexpr int CLUSTER_BLOCK = PTP_CLUSTER_BLOCK; // cluster single-solve kernel: 1 CTA per SM (BFS cluster + sweep team)
 constexpr int SOLVE_BLOCK = 1024;  // threads per CTA, cooperative sweep kernel (one pass per iteration on C3-size windows)
 template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
 template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
@@ -156,6 +160,51 @@ __global__ void k_ring_check(const u32 *__restrict__ ring8, const u32 *__restric
     if (bad) atomicAdd(counters + 2, (ull)bad);
 }
 
+// Geometry table (MeshView::geo): for ring slot k of vertex v, the inverse Gram matrix of triangle k = (v, n_k, n_{k+1})
+// and |X_k|, computed with the very operations of update_step (src/geodesics_ptp.cpp:208-231, 257-258) so that a
+// relaxation reading the table produces the same bits as one recomputing them. One thread per vertex; rows in the
+// overflow pool (one-rings longer than 8) are not covered (their relaxation recomputes the geometry).
+template <class R>
+__global__ void k_geo_build(const typename Ops<R>::vec4 *__restrict__ GT4, const u32 *__restrict__ ring8, u32 V,
+                            typename Ops<R>::vec4 *__restrict__ geo)
+{
+    typedef Ops<R> O;
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const u32 *row = ring8 + (size_t)v * GL;
+    R *out = reinterpret_cast<R *>(geo + (size_t)v * GL);
+    u32 e[GL];
+    for (u32 k = 0; k < GL; k++) e[k] = row[k];
+    u32 len = 0;
+    bool open = false;
+    if (e[0] != OVF && e[0] != NIL) {
+        open = (e[0] & OPEN_BIT) != 0;
+        e[0] &= ~OPEN_BIT;
+        while (len < GL && e[len] != NIL) len++;
+    }
+    const u32 n_tri = len == 0 ? 0 : (open ? len - 1 : len);
+    const P3<R> Ps = load_pos<R>(GT4 + v);
+    P3<R> X[GL];
+    R q[GL];
+    for (u32 k = 0; k < len; k++) {
+        const P3<R> Pn = load_pos<R>(GT4 + e[k]);
+        X[k] = {O::sub(Pn.x, Ps.x), O::sub(Pn.y, Ps.y), O::sub(Pn.z, Ps.z)};
+        q[k] = dot3(X[k], X[k]);
+    }
+    for (u32 k = 0; k < GL; k++) {
+        R rec[4] = {R(0), R(0), R(0), R(0)};
+        if (k < len) {
+            rec[3] = O::sqrt(q[k]);
+            if (k < n_tri) {
+                const u32 k1 = k + 1 < len ? k + 1 : 0;
+                const TriQ<R> Q = tri_geom<R>(X[k], X[k1], q[k], q[k1]);
+                rec[0] = Q.Q00; rec[1] = Q.Q01; rec[2] = Q.Q11;
+            }
+        }
+        for (u32 c = 0; c < 4; c++) out[k * 4 + c] = rec[c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // CHE construction on the device (reference: che::update_evt_ot_et, src/che.cpp:1295-1362, serial, ~22 s at
 // 10 M vertices). Directed edges (a -> b) go into an open-addressing hash table keyed by (a << 32 | b);
@@ -228,6 +277,7 @@ template <class R>
 __global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 kcap, u32 sent, ull *bar)
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
     bfs_run<R, TeamGrid, false>(t, m, w, sources, S, kcap, sent);
 }
 
@@ -239,6 +289,7 @@ k_geodesics_merged(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_
 {
     extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
     BfsHook<R, TeamGrid> hook(t, m, w, sent, bfs_threads);
     hook.b.init(sources, S);
     const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false, BfsHook<R, TeamGrid>>(
@@ -251,6 +302,7 @@ template <class R>
 __global__ void __launch_bounds__(FUSED_BLOCK, 2) k_dbg_producer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 sent, ull *bar)
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
     bfs_run<R, TeamGrid, true>(t, m, w, sources, S, NIL, sent);
 }
 template <class R>
@@ -258,6 +310,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 2)
 k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 sent, ull *bar)
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
     const u32 d = ptp_run<R, TeamGrid, false, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, false>(t, m, w, d, dist_out, nullptr, 0u);
 }
@@ -268,6 +321,15 @@ __global__ void k_dbg_barriers(ull *bar, u32 n, u32 *sink)
     TeamGrid t{bar, 0, 0, gridDim.x};
     u32 acc = 0;
     for (u32 i = 0; i < n; i++) acc += t.sync(i & 1u);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *sink = acc;
+}
+
+// DEBUG / measurement: n hardware cluster barriers and nothing else (PTP_CLUSTER_BARRIER in ptp_debug_barrier_ns)
+__global__ void k_dbg_cluster_barriers(u32 n, u32 *sink)
+{
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    u32 acc = 0;
+    for (u32 i = 0; i < n; i++) { cl.sync(); acc += i; }
     if (threadIdx.x == 0 && blockIdx.x == 0) *sink = acc;
 }
 
@@ -297,6 +359,7 @@ k_solve_grid(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u
 {
     extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
     const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
     const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false>(t, m, w, sources, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
                                                                staged ? ptp_dyn_smem : nullptr);
@@ -314,6 +377,7 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
     extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     if (blockIdx.x < nb) {
         TeamGrid t{bar, 0, 0, nb};
+        t.err = w.ctrl + C_ERROR;
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
         bfs_run<R, TeamGrid, true>(t, m, w, sources, S, NIL, sent);
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
@@ -326,8 +390,40 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
     }
 }
 
+// Single solve, one launch of thread-block clusters: cluster 0 (CTAs [0, nb)) builds the toplesets with hardware cluster
+// barriers (bfs_run_cluster), every other CTA belongs to the sweep team (one CTA per SM, window staged in shared
+// memory) that lays out and relaxes the levels as they appear. The sweep team also presets the BFS tables (all-ones:
+// key = ~0, inv = NIL) while the BFS cluster waits for C_FILLED, so the whole solve stays one launch.
+template <class R, bool CL>
+__global__ void __launch_bounds__(CLUSTER_BLOCK, 1)
+k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb,
+                    u32 staged, u32 bfs_flags)
+{
+    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
+    if (blockIdx.x < nb) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
+        bfs_run_cluster<R, true>(m, w, sources, S, bfs_flags);
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
+    } else {
+        TeamGrid t{bar + 64, 0, nb, gridDim.x - nb};
+        t.err = w.ctrl + C_ERROR;
+        const u32 tid = t.cta() * blockDim.x + threadIdx.x, nth = t.nctas() * blockDim.x;
+        uint4 *key4 = reinterpret_cast<uint4 *>(w.key); // V * 8 bytes, 16-byte aligned (cudaMalloc)
+        const uint4 ones = make_uint4(NIL, NIL, NIL, NIL);
+        for (u32 i = tid; i < m.V / 2; i += nth) key4[i] = ones;
+        if (tid == 0 && (m.V & 1u)) w.key[m.V - 1] = ~0ull;
+        for (u32 v = tid; v < m.V; v += nth) w.inv[v] = NIL;
+        t.sync();
+        if (tid == 0) flag_store(w.ctrl + C_FILLED, 1ull);
+        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
+                                                                  staged ? ptp_dyn_smem : nullptr);
+        scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
+        if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
+    }
+}
+
 // one CTA per solve, CTAs pull source sets from a queue
-template <class R>
+template <class R, bool GEO>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
 k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
           ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */)
@@ -344,7 +440,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         __syncthreads();
         if (b >= B) {
             // no solve left for this CTA: lend its threads to the relax passes of the solves still running
-            if (descs) help_loop<R>(works, descs, gridDim.x, counters, counters + 1, B);
+            if (descs) help_loop<R, GEO>(m.geo, works, descs, gridDim.x, counters, counters + 1, B);
             break;
         }
         const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
@@ -358,8 +454,8 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         layout_rows_thread<R>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
         __syncthreads();
         const ull t2 = global_timer();
-        const u32 d = ptp_run<R, TeamCta, false, 1, false>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr,
-                                                          (NoHook *)nullptr, help, counters);
+        const u32 d = ptp_run<R, TeamCta, false, 1, false, NoHook, GEO>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr,
+                                                                       (NoHook *)nullptr, help, counters);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -430,6 +526,7 @@ struct ptp_mesh {
     u32 *ring8 = nullptr;
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
+    void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
     u64 bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -479,6 +576,7 @@ template <class R> MeshView<R> mesh_view(const ptp_mesh *m)
     v.GT4 = (const typename Ops<R>::vec4 *)m->GT4;
     v.ring8 = m->ring8;
     v.ovf = m->ovf;
+    v.geo = (const typename Ops<R>::vec4 *)m->geo;
     return v;
 }
 
@@ -679,6 +777,76 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     return PTP_OK;
 }
 
+// PTP_FUSED=4 (default when the device can co-schedule the clusters): BFS on one thread-block cluster + sweep team.
+// Returns PTP_OK and sets *launched = false when the configuration is not available (caller falls back).
+int cluster_size()
+{
+    static int v = [] { const char *e = getenv("PTP_CLUSTER"); return e ? atoi(e) : 8; }();
+    return std::max(1, std::min(v, 16));
+}
+
+template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, bool *launched)
+{
+    *launched = false;
+    MeshView<R> mv = mesh_view<R>(m);
+    Work<R> w = work_view<R>(m);
+    if (!cl) w.cl[0] = w.cl[1] = nullptr;
+    void *fn = cl ? (void *)k_geodesics_cluster<R, true> : (void *)k_geodesics_cluster<R, false>;
+    // the staged window needs (window + entering topleset) <= groups of the sweep team; with ~110 sweep CTAs the widest
+    // C3 windows do not fit and the streamed sweep measured faster unstaged (27.9 vs 29.0 ms): PTP_STAGE=1 turns it on
+    static const bool want_stage = [] { const char *e = getenv("PTP_STAGE"); return e && atoi(e) == 1; }();
+    u32 staged = (want_stage && PTP_GRID_MAP == 4) ? 1u : 0u;
+    size_t smem = staged ? CLUSTER_BLOCK * Stage4<R>::bytes_per_thread() : 0;
+    const int csize = cluster_size();
+    if (csize > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return PTP_OK;
+    }
+    if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = (unsigned)csize;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.blockDim = dim3(CLUSTER_BLOCK);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    cfg.gridDim = dim3((unsigned)(m->num_sms / csize * csize));
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, fn, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return PTP_OK;
+    }
+    // every CTA must be resident at once (software grid barrier of the sweep team + the BFS cluster it waits for)
+    const int grid = std::min(n_clusters, m->num_sms / csize) * csize;
+    if (grid < csize + 16) return PTP_OK;
+    cfg.gridDim = dim3((unsigned)grid);
+    const u32 *src = (const u32 *)m->w_src;
+    R *out = (R *)m->w_out;
+    u32 *clo = (u32 *)m->w_clout;
+    ull *bar = (ull *)m->w_bar;
+    u32 sent = (u32)(m->V + m->ws_scap);
+    u32 nb = (u32)csize;
+    static const u32 bfs_flags_env = [] { const char *e = getenv("PTP_BFS_FLAGS"); return e ? (u32)atoi(e) : 0u; }();
+    u32 bfs_flags = bfs_flags_env;
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb, &staged, &bfs_flags};
+    CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] cluster launch refused (%s): falling back to the two-team kernel\n", cudaGetErrorString(e));
+        return PTP_OK;
+    }
+    if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] cluster kernel: grid %d, cluster %d, staged %u, smem %zu\n", grid, csize, staged, smem);
+    *launched = true;
+    return PTP_OK;
+}
+
 void fill_stats(const ptp_mesh *m, ptp_stats_t *st, u64 launches, double ms_top, double ms_solve, double ms_total)
 {
     if (!st) return;
@@ -837,6 +1005,12 @@ int fetch_ctrl(ptp_mesh *m)
 {
     CK(cudaMemcpyAsync(m->h_ctrl, m->w_ctrl, 8 * C_COUNT, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
+    const ull wd = ((const ull *)m->h_ctrl)[C_ERROR];
+    if (wd) {
+        static const char *what[] = {"", "grid barrier", "sweep team waiting for toplesets / rows", "layout warp waiting for the BFS",
+                                     "layout warp waiting for its turn to publish", "BFS cluster waiting for its tables", "elastic relax chunks"};
+        return fail(PTP_ERR_CUDA, std::string("device watchdog: a wait did not complete (") + (wd < 7 ? what[wd] : "?") + "); results discarded");
+    }
     return PTP_OK;
 }
 
@@ -912,7 +1086,8 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     int rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
-    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 1; }();
+    // PTP_FUSED: 4 (default) cluster BFS + sweep team, 1 two-team kernel, 0 three launches, 2 / 3 debug variants
+    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 4; }();
     if (dbg == 2 && !cl) {
         MeshView<R> mv = mesh_view<R>(m);
         Work<R> w = work_view<R>(m);
@@ -954,7 +1129,9 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
         return PTP_OK;
     }
     if (use_fused()) {
-        if ((rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
+        bool launched = false;
+        if (dbg != 1 && (rc = launch_cluster<R>(m, S, cl, cl_fill, &launched))) return rc; // PTP_FUSED=1: the two-team kernel
+        if (!launched && (rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
         CK(cudaEventRecord(m->ev[1], m->stream));
         CK(cudaEventRecord(m->ev[2], m->stream));
         return PTP_OK;
@@ -995,7 +1172,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         const ull *c = (const ull *)m->h_ctrl;
         const double t_bfs = c[C_TBFS] > c[C_TSTART] ? (c[C_TBFS] - c[C_TSTART]) * 1e-6 : 0.0;
         const double t_all = ev_ms(m->ev[0], m->ev[2]);
-        if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] producer polls by the sweep team: %llu\n", c[C_ARGMAX]);
+        if (getenv("PTP_DEBUG")) {
+            fprintf(stderr, "[ptp] producer polls by the sweep team: %llu\n", c[C_ARGMAX]);
+            if (c[C_TPHASE + 6]) fprintf(stderr, "[ptp] sweep thread-0 ms: relax %.2f | wait for producers %.2f | barrier %.2f | post-barrier %.2f\n",
+                    c[C_TPHASE + 6] * 1e-6, c[C_TPHASE + 7] * 1e-6, c[C_TPHASE + 8] * 1e-6, c[C_TPHASE + 9] * 1e-6);
+            if (c[C_TPHASE])
+                fprintf(stderr, "[ptp] cluster BFS thread-0 ms: claim %.2f | barrier1 %.2f | publish %.2f | own+scan %.2f | barrier2 %.2f | place+barrier3 %.2f\n",
+                        c[C_TPHASE] * 1e-6, c[C_TPHASE + 1] * 1e-6, c[C_TPHASE + 5] * 1e-6, c[C_TPHASE + 2] * 1e-6, c[C_TPHASE + 3] * 1e-6, c[C_TPHASE + 4] * 1e-6);
+        }
         fill_stats(m, st, 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
     } else
         fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
@@ -1011,7 +1195,7 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
         free_list(m, m->bt_allocs);
         m->bt_slots = 0;
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R>, BatchCfg<R>::BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R, true>, BatchCfg<R>::BLOCK, 0));
         if (per_sm < 1) return fail(PTP_ERR_CUDA, "batched kernel does not fit on an SM");
         const u32 slots = (u32)(m->num_sms * per_sm);
         const u64 V = m->V, scap = std::max<u64>(max_s, 16), N = V + scap;
@@ -1105,6 +1289,15 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         chunk = std::max<u64>(1, std::min<u64>(B, budget / (sizeof(R) * m->V)));
     }
     if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V))) return rc;
+    // Geometry table: mesh-constant half of update_step, shared by every solve of every batch on this mesh
+    // (PTP_GEO=0 keeps the relaxations self-contained: A/B runs, or meshes whose table would not fit)
+    static const bool use_geo = [] { const char *e = getenv("PTP_GEO"); return e ? atoi(e) != 0 : true; }();
+    if (use_geo && !m->geo) {
+        if ((rc = dev_alloc(m, &m->geo, 4 * sizeof(R) * GL * m->V, nullptr))) return rc;
+        k_geo_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V,
+                                                                          (typename Ops<R>::vec4 *)m->geo);
+        CK(cudaGetLastError());
+    }
     CK(cudaMemcpyAsync(m->bt_src, sources, 4 * n_src, cudaMemcpyHostToDevice, stream));
     if (offsets) CK(cudaMemcpyAsync(m->bt_off, offsets, 8 * (u64)(B + 1), cudaMemcpyHostToDevice, stream));
     ull *queue = (ull *)m->bt_queue;
@@ -1122,9 +1315,10 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         u32 *counters = (u32 *)((char *)m->bt_help + sizeof(HelpDesc) * m->bt_slots);
         if (elastic) CK(cudaMemsetAsync(m->bt_help, 0, sizeof(HelpDesc) * m->bt_slots + 64, stream));
         const u32 grid = elastic ? m->bt_slots : std::min<u32>(m->bt_slots, nb);
-        k_batched<R><<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
-                                                        offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
-                                                        (u32)(m->V + m->bt_scap), queue, queue + 1, descs, counters);
+        auto kern = mv.geo ? k_batched<R, true> : k_batched<R, false>;
+        kern<<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
+                                                   offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
+                                                   (u32)(m->V + m->bt_scap), queue, queue + 1, descs, counters);
         CK(cudaGetLastError());
         launches++;
         if (!on_device)
@@ -1294,6 +1488,20 @@ double ptp_debug_barrier_ns(int ctas, int block, int n)
     for (int rep = 0; rep < 3; rep++) {
         cudaMemset(bar, 0, 1024);
         cudaEventRecord(e0);
+        if (ctas < 0) { // hardware barrier of ONE thread-block cluster of -ctas CTAs
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)-ctas;
+            at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned)-ctas);
+            cfg.blockDim = dim3(block);
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (-ctas > 8) cudaFuncSetAttribute((void *)k_dbg_cluster_barriers, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            void *cargs[] = {&nn, &sink};
+            if (cudaLaunchKernelExC(&cfg, (void *)k_dbg_cluster_barriers, cargs) != cudaSuccess) { cudaGetLastError(); best = -1; break; }
+        } else
         if (cudaLaunchCooperativeKernel((void *)k_dbg_barriers, dim3(ctas), dim3(block), args, 0, nullptr) != cudaSuccess) { best = -1; break; }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
@@ -1315,6 +1523,7 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     cudaFree(m->GT4);
     cudaFree(m->ring8);
     cudaFree(m->ovf);
+    cudaFree(m->geo);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     for (auto &e : m->ev)
         if (e) cudaEventDestroy(e);

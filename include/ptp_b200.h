@@ -152,7 +152,8 @@ int ptp_farthest_point_sampling_f64(ptp_mesh_t *mesh, uint32_t *samples, uint32_
                                     double radio, uint32_t *n_out, double *max_dist, ptp_stats_t *stats);
 
 /* Measurement helper, not part of the reference interface: nanoseconds per grid barrier (the fused
- * arrive + reduce + poll barrier of the single-solve kernels) for `ctas` CTAs of `block` threads; < 0 on error. */
+ * arrive + reduce + poll barrier of the single-solve kernels) for `ctas` CTAs of `block` threads; < 0 on error.
+ * ctas < 0 measures the hardware barrier of ONE thread-block cluster of -ctas CTAs instead (BFS team). */
 double ptp_debug_barrier_ns(int ctas, int block, int n);
 
 #ifdef __cplusplus

@@ -354,6 +354,7 @@ def run_single(args, api, torch, peak, peak_src):
         st = dm.last_stats
         dev_ms.append(st["ms_total"]); top_ms.append(st["ms_toplesets"]); sol_ms.append(st["ms_solve"])
     st = dm.last_stats
+    kernel = dm.last_kernel
     ms = statistics.median(dev_ms)
     sweep_ms = statistics.median(sol_ms)
     achieved = st["vertex_updates"] * BYTES_PER_UPDATE[8] / (ms / 1e3) / 1e9
@@ -361,15 +362,15 @@ def run_single(args, api, torch, peak, peak_src):
     _, _, manifold, che_ms = api.che_build(mesh.VT, V, torch.cuda.current_device())
     che_wall = time.perf_counter() - t
     res = {
-        "workload": wl, "ms_per_solve": ms, "ms_bfs_team": statistics.median(top_ms), "ms_until_sweep_team_done": sweep_ms,
+        "workload": wl, "kernel": kernel, "ms_per_solve": ms, "ms_bfs_team": statistics.median(top_ms), "ms_until_sweep_team_done": sweep_ms,
         "che_build": {"device_ms": che_ms, "ms_with_h2d_d2h": che_wall * 1e3, "manifold": manifold,
                       "note": "OT/EVT from the face list on the device (reference: che::update_evt_ot_et, serial)"},
         "vertex_updates": st["vertex_updates"], "relaxations": st["relaxations"], "iterations": st["iterations"], "levels": st["n_levels"],
         "max_window": st["max_window"], "vertex_updates_per_s": st["vertex_updates"] / (ms / 1e3),
         "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
         "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],
-        "roofline": {"bound": "hbm", "kernel": "k_geodesics_fused<double> (BFS team + sweep team, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_geodesics_fused_f64_c3"), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": kernel + " (BFS team + sweep team, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(kernel.split("<")[0] + "_f64_c3"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[8],
                      "note": "latency-bound by construction: ~#toplesets dependent iterations (SURVEY.md §0.4)"},
     }

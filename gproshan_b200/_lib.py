@@ -33,7 +33,7 @@ class Stats(C.Structure):
 # every symbol include/ptp_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "ptp_last_error", "ptp_device_count", "ptp_version", "ptp_host_alloc", "ptp_host_free",
-    "ptp_mesh_create_f32", "ptp_mesh_create_f64", "ptp_mesh_destroy", "ptp_che_build", "ptp_mesh_n_vertices",
+    "ptp_mesh_create_f32", "ptp_mesh_create_f64", "ptp_mesh_destroy", "ptp_mesh_last_kernel", "ptp_che_build", "ptp_mesh_n_vertices",
     "ptp_mesh_n_half_edges", "ptp_mesh_real_size", "ptp_mesh_device", "ptp_mesh_device_bytes",
     "ptp_toplesets", "ptp_solve_f32", "ptp_solve_f64", "ptp_geodesics_f32", "ptp_geodesics_f64",
     "ptp_solve_batched_f32", "ptp_solve_batched_f64",
@@ -75,6 +75,8 @@ def lib():
     L.ptp_che_build.argtypes = [u32p, C.c_uint64, C.c_uint64, u32p, u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.ptp_debug_barrier_ns.argtypes = [C.c_int, C.c_int, C.c_int]
     L.ptp_debug_barrier_ns.restype = C.c_double
+    L.ptp_mesh_last_kernel.argtypes = [vp]
+    L.ptp_mesh_last_kernel.restype = C.c_char_p
     L.ptp_mesh_destroy.argtypes = [vp]
     L.ptp_mesh_destroy.restype = None
     for n in ("ptp_mesh_n_vertices", "ptp_mesh_n_half_edges", "ptp_mesh_device_bytes"):

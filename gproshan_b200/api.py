@@ -97,6 +97,11 @@ class DeviceMesh:
         self.close()
 
     @property
+    def last_kernel(self) -> str:
+        """dominant kernel of the last call on this mesh (which single-solve variant ran)"""
+        return _lib.lib().ptp_mesh_last_kernel(self._h).decode()
+
+    @property
     def device_bytes(self) -> int:
         return _lib.lib().ptp_mesh_device_bytes(self._h)
 

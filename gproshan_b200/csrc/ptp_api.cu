@@ -527,6 +527,7 @@ struct ptp_mesh {
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
+    const char *last_kernel = ""; // dominant kernel of the last call on this mesh (ptp_mesh_last_kernel)
     u64 bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -726,6 +727,7 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged};
     CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
     CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SOLVE_BLOCK), args, smem, m->stream));
+    m->last_kernel = sizeof(R) == 8 ? "k_solve_grid<double>" : "k_solve_grid<float>";
     return PTP_OK;
 }
 
@@ -774,6 +776,7 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb, &staged};
     CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
     CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FUSED_BLOCK), args, smem, m->stream));
+    m->last_kernel = sizeof(R) == 8 ? "k_geodesics_fused<double>" : "k_geodesics_fused<float>";
     return PTP_OK;
 }
 
@@ -844,6 +847,7 @@ template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, 
     }
     if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] cluster kernel: grid %d, cluster %d, staged %u, smem %zu\n", grid, csize, staged, smem);
     *launched = true;
+    m->last_kernel = sizeof(R) == 8 ? "k_geodesics_cluster<double>" : "k_geodesics_cluster<float>";
     return PTP_OK;
 }
 
@@ -1289,9 +1293,11 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         chunk = std::max<u64>(1, std::min<u64>(B, budget / (sizeof(R) * m->V)));
     }
     if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V))) return rc;
-    // Geometry table: mesh-constant half of update_step, shared by every solve of every batch on this mesh
-    // (PTP_GEO=0 keeps the relaxations self-contained: A/B runs, or meshes whose table would not fit)
-    static const bool use_geo = [] { const char *e = getenv("PTP_GEO"); return e ? atoi(e) != 0 : true; }();
+    // Geometry table (PTP_GEO=1): the mesh-constant half of update_step (3 of 4 divisions, 2 of 3 square roots) read from
+    // a table shared by every solve instead of recomputed. Bit-exact, 25 % fewer instructions per relaxation, and yet
+    // measured SLOWER in float (C5: 229-234 vs 239-241 sources/s: +128 B of DRAM traffic per relaxation on a kernel that
+    // is bound by memory latency, not issue slots) and only +4 % in double, so it stays opt-in.
+    static const bool use_geo = [] { const char *e = getenv("PTP_GEO"); return e ? atoi(e) != 0 : false; }();
     if (use_geo && !m->geo) {
         if ((rc = dev_alloc(m, &m->geo, 4 * sizeof(R) * GL * m->V, nullptr))) return rc;
         k_geo_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V,
@@ -1320,6 +1326,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
                                                    offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
                                                    (u32)(m->V + m->bt_scap), queue, queue + 1, descs, counters);
         CK(cudaGetLastError());
+        m->last_kernel = sizeof(R) == 8 ? "k_batched<double>" : "k_batched<float>";
         launches++;
         if (!on_device)
             CK(cudaMemcpyAsync(rows + first * m->V, m->bt_rows, sizeof(R) * (u64)nb * m->V, cudaMemcpyDeviceToHost, stream));
@@ -1531,6 +1538,7 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     delete m;
 }
 
+const char *ptp_mesh_last_kernel(const ptp_mesh_t *m) { return m ? m->last_kernel : ""; }
 uint64_t ptp_mesh_n_vertices(const ptp_mesh_t *m) { return m ? m->V : 0; }
 uint64_t ptp_mesh_n_half_edges(const ptp_mesh_t *m) { return m ? m->H : 0; }
 int ptp_mesh_real_size(const ptp_mesh_t *m) { return m ? m->real_size : 0; }

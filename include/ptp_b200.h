@@ -77,6 +77,8 @@ int ptp_mesh_create_f32(const float *GT, const uint32_t *VT, const uint32_t *OT,
 int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
                         uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
 void ptp_mesh_destroy(ptp_mesh_t *mesh);
+/* name of the dominant kernel of the last solve on this mesh (measurement: which single-solve variant ran) */
+const char *ptp_mesh_last_kernel(const ptp_mesh_t *mesh);
 
 /* CHE tables from a face list, on the device. Replaces che::update_evt_ot_et (src/che.cpp:1295-1362; serial,
  * ~22 s at 10 M vertices) for oriented edge-manifold input, for which OT / EVT equal the reference's bit for

@@ -327,7 +327,7 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_ref_gpu:
         torch.cuda.synchronize()
         if "single_source" in line:
-            line["single_source"]["reference_gpu"] = reference_gpu_leg("c3", args.quick, 1, True)
+            line["single_source"]["reference_gpu"] = reference_gpu_leg("c3", args.quick, 3, True)
         line["reference_gpu"] = reference_gpu_leg("c5", args.quick, 3, False)
     if rank == 0:
         print(json.dumps(line), flush=True)

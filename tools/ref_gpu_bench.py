@@ -84,13 +84,13 @@ def run(workload, quick, n_sources, coalescence, check):
     top, srt, lim = rc.compute_toplesets(srcs[:1])
     gpu_solve(ol, ref, rc, srcs[:1], lim, srt, False)
     for k in range(n_sources):
-        src = np.ascontiguousarray(srcs[k:k + 1])
+        src = np.ascontiguousarray(srcs[k % srcs.size:k % srcs.size + 1])  # (c3 has one source: repeated solves)
         t = time.perf_counter()
         top, srt, lim = rc.compute_toplesets(src)
         top_ms = (time.perf_counter() - t) * 1e3
         d, gpu_ms, wall_ms = gpu_solve(ol, ref, rc, src, lim, srt, False)
         rec = {"toplesets_cpu_ms": top_ms, "gpu_ms": gpu_ms, "wall_ms": wall_ms, "levels": int(lim.size - 1)}
-        if coalescence:
+        if coalescence and k == 0:
             dc, g2, w2 = gpu_solve(ol, ref, rc, src, lim, srt, True)
             rec["coalescence"] = {"gpu_ms": g2, "wall_ms": w2, "max_rel_vs_plain_gpu": rel_err(dc, d)}
         if check and k == 0:
@@ -102,6 +102,7 @@ def run(workload, quick, n_sources, coalescence, check):
     g = [s["gpu_ms"] for s in out["solves"]]
     tt = [s["toplesets_cpu_ms"] + s["wall_ms"] for s in out["solves"]]
     out["gpu_ms_per_solve"] = float(np.median(g))
+    out["gpu_ms_best"] = float(min(g))
     out["ms_per_solve_with_cpu_toplesets"] = float(np.median(tt))
     out["sources_per_s"] = 1e3 * len(tt) / float(sum(tt))
     return out

@@ -316,11 +316,26 @@ k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out,
 }
 
 // DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
-__global__ void k_dbg_barriers(ull *bar, u32 n, u32 *sink)
+// mode 0: barriers only. mode 1: every iteration each CTA writes a word, barrier, every thread reads the word its
+// neighbour CTA wrote (plain load: the acquire barrier flushed L1) and the value feeds the next iteration — the
+// barrier + one dependent L2 round trip of a PTP iteration. mode 2: same with a poll that does not acquire (no
+// CCTL.IVALL) and an ld.cg read.
+__global__ void k_dbg_barriers(ull *bar, u32 n, u32 *sink, u32 mode)
 {
     TeamGrid t{bar, 0, 0, gridDim.x};
+    t.relaxed_poll = mode == 2u ? 1u : 0u;
+    u32 *box = reinterpret_cast<u32 *>(bar + 16); // [gridDim.x] words after the barrier words (bar is 4 KB)
     u32 acc = 0;
-    for (u32 i = 0; i < n; i++) acc += t.sync(i & 1u);
+    for (u32 i = 0; i < n; i++) {
+        if (mode) {
+            if (threadIdx.x == 0) box[blockIdx.x] = i + acc;
+        }
+        acc += t.sync(i & 1u);
+        if (mode) {
+            const u32 *p = box + (blockIdx.x + 1u) % gridDim.x;
+            acc += (mode == 2u ? __ldcg(p) : *(const volatile u32 *)p) & 1u;
+        }
+    }
     if (threadIdx.x == 0 && blockIdx.x == 0) *sink = acc;
 }
 
@@ -394,7 +409,7 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
 // barriers (bfs_run_cluster), every other CTA belongs to the sweep team (one CTA per SM, window staged in shared
 // memory) that lays out and relaxes the levels as they appear. The sweep team also presets the BFS tables (all-ones:
 // key = ~0, inv = NIL) while the BFS cluster waits for C_FILLED, so the whole solve stays one launch.
-template <class R, bool CL>
+template <class R, bool CL, bool GEO>
 __global__ void __launch_bounds__(CLUSTER_BLOCK, 1)
 k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb,
                     u32 staged, u32 bfs_flags)
@@ -415,8 +430,8 @@ k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist
         for (u32 v = tid; v < m.V; v += nth) w.inv[v] = NIL;
         t.sync();
         if (tid == 0) flag_store(w.ctrl + C_FILLED, 1ull);
-        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
-                                                                  staged ? ptp_dyn_smem : nullptr);
+        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true, NoHook, GEO>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048,
+                                                                               m.ring_symmetric != 0, staged ? ptp_dyn_smem : nullptr);
         scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
         if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
     }
@@ -527,6 +542,7 @@ struct ptp_mesh {
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
+    bool geo_failed = false; // the table did not fit: do not try again
     const char *last_kernel = ""; // dominant kernel of the last call on this mesh (ptp_mesh_last_kernel)
     u64 bytes = 0;
     cudaStream_t stream = nullptr;
@@ -788,13 +804,43 @@ int cluster_size()
     return std::max(1, std::min(v, 16));
 }
 
+// Geometry table (MeshView::geo), built once per mesh on first use. Not fatal when it does not fit: the kernels then
+// recompute the geometry (`*ok` = false).
+template <class R> int ensure_geo(ptp_mesh *m, cudaStream_t stream, bool *ok)
+{
+    *ok = m->geo != nullptr;
+    if (m->geo || m->geo_failed) return PTP_OK;
+    const size_t bytes = 4 * sizeof(R) * GL * m->V;
+    if (cudaMalloc(&m->geo, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        m->geo = nullptr;
+        m->geo_failed = true;
+        return PTP_OK;
+    }
+    m->bytes += bytes;
+    k_geo_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V,
+                                                                      (typename Ops<R>::vec4 *)m->geo);
+    CK(cudaGetLastError());
+    *ok = true;
+    return PTP_OK;
+}
+
 template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, bool *launched)
 {
     *launched = false;
+    // Single solve with the geometry table (PTP_GEO_SINGLE=1, off): takes 3 divisions + 2 square roots per triangle off
+    // the dependent FP chain of an iteration (thread-0 stamps on C3: compute 3.2 -> 2.1 us per iteration) but the two
+    // extra 32-byte records per lane lengthen the gather phase by as much (1.05 -> 2.0 us): 30.1 vs 28.5 ms per solve.
+    static const bool want_geo = [] { const char *e = getenv("PTP_GEO_SINGLE"); return e ? atoi(e) != 0 : false; }();
+    bool geo = false;
+    int rc;
+    if (want_geo && (rc = ensure_geo<R>(m, m->stream, &geo))) return rc;
     MeshView<R> mv = mesh_view<R>(m);
+    if (!geo) mv.geo = nullptr;
     Work<R> w = work_view<R>(m);
     if (!cl) w.cl[0] = w.cl[1] = nullptr;
-    void *fn = cl ? (void *)k_geodesics_cluster<R, true> : (void *)k_geodesics_cluster<R, false>;
+    void *fn = geo ? (cl ? (void *)k_geodesics_cluster<R, true, true> : (void *)k_geodesics_cluster<R, false, true>)
+                   : (cl ? (void *)k_geodesics_cluster<R, true, false> : (void *)k_geodesics_cluster<R, false, false>);
     // the staged window needs (window + entering topleset) <= groups of the sweep team; with ~110 sweep CTAs the widest
     // C3 windows do not fit and the streamed sweep measured faster unstaged (27.9 vs 29.0 ms): PTP_STAGE=1 turns it on
     static const bool want_stage = [] { const char *e = getenv("PTP_STAGE"); return e && atoi(e) == 1; }();
@@ -1180,6 +1226,16 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
             fprintf(stderr, "[ptp] producer polls by the sweep team: %llu\n", c[C_ARGMAX]);
             if (c[C_TPHASE + 6]) fprintf(stderr, "[ptp] sweep thread-0 ms: relax %.2f | wait for producers %.2f | barrier %.2f | post-barrier %.2f\n",
                     c[C_TPHASE + 6] * 1e-6, c[C_TPHASE + 7] * 1e-6, c[C_TPHASE + 8] * 1e-6, c[C_TPHASE + 9] * 1e-6);
+#ifdef PTP_PHASE_TIMERS
+            {
+                ull t[16];
+                cudaMemcpyFromSymbol(t, g_dbg_t, sizeof t);
+                fprintf(stderr, "[ptp] sweep CTA-0 thread-0 cumulative ms: top %.2f | row %.2f | gathers %.2f | compute %.2f | min+commit %.2f | stamps %.2f | rest %.2f | publish %.2f | barrier %.2f | post %.2f\n",
+                        t[0] * 1e-6, t[1] * 1e-6, t[2] * 1e-6, t[3] * 1e-6, t[4] * 1e-6, t[5] * 1e-6, t[6] * 1e-6, t[7] * 1e-6, t[8] * 1e-6, t[9] * 1e-6);
+                ull z[16] = {0};
+                cudaMemcpyToSymbol(g_dbg_t, z, sizeof z);
+            }
+#endif
             if (c[C_TPHASE])
                 fprintf(stderr, "[ptp] cluster BFS thread-0 ms: claim %.2f | barrier1 %.2f | publish %.2f | own+scan %.2f | barrier2 %.2f | place+barrier3 %.2f\n",
                         c[C_TPHASE] * 1e-6, c[C_TPHASE + 1] * 1e-6, c[C_TPHASE + 5] * 1e-6, c[C_TPHASE + 2] * 1e-6, c[C_TPHASE + 3] * 1e-6, c[C_TPHASE + 4] * 1e-6);
@@ -1298,18 +1354,15 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     // measured SLOWER in float (C5: 229-234 vs 239-241 sources/s: +128 B of DRAM traffic per relaxation on a kernel that
     // is bound by memory latency, not issue slots) and only +4 % in double, so it stays opt-in.
     static const bool use_geo = [] { const char *e = getenv("PTP_GEO"); return e ? atoi(e) != 0 : false; }();
-    if (use_geo && !m->geo) {
-        if ((rc = dev_alloc(m, &m->geo, 4 * sizeof(R) * GL * m->V, nullptr))) return rc;
-        k_geo_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V,
-                                                                          (typename Ops<R>::vec4 *)m->geo);
-        CK(cudaGetLastError());
-    }
+    bool geo_ok = false;
+    if (use_geo && (rc = ensure_geo<R>(m, stream, &geo_ok))) return rc;
     CK(cudaMemcpyAsync(m->bt_src, sources, 4 * n_src, cudaMemcpyHostToDevice, stream));
     if (offsets) CK(cudaMemcpyAsync(m->bt_off, offsets, 8 * (u64)(B + 1), cudaMemcpyHostToDevice, stream));
     ull *queue = (ull *)m->bt_queue;
     CK(cudaMemsetAsync(queue, 0, 128, stream));
     CK(cudaEventRecord(m->ev[0], stream));
     MeshView<R> mv = mesh_view<R>(m);
+    if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
     u64 launches = 0;
     for (u64 first = 0; first < B; first += chunk) {
         const u32 nb = (u32)std::min<u64>(chunk, B - first);
@@ -1486,14 +1539,17 @@ double ptp_debug_barrier_ns(int ctas, int block, int n)
     ull *bar = nullptr;
     u32 *sink = nullptr;
     cudaEvent_t e0, e1;
-    if (cudaMalloc(&bar, 1024) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) return -1;
+    // block >= 100000 selects a measurement mode: block = mode * 100000 + threads (see k_dbg_barriers)
+    u32 mode = (u32)(block / 100000);
+    block %= 100000;
+    if (cudaMalloc(&bar, 4096) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) return -1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     u32 nn = (u32)n;
-    void *args[] = {&bar, &nn, &sink};
+    void *args[] = {&bar, &nn, &sink, &mode};
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
-        cudaMemset(bar, 0, 1024);
+        cudaMemset(bar, 0, 4096);
         cudaEventRecord(e0);
         if (ctas < 0) { // hardware barrier of ONE thread-block cluster of -ctas CTAs
             cudaLaunchConfig_t cfg = {};

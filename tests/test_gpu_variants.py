@@ -19,7 +19,7 @@ VARIANTS = [
     ("two-team-staged", {"PTP_FUSED": "1", "PTP_STAGE": "2"}, "k_geodesics_fused"),
     ("three-launches", {"PTP_FUSED": "0"}, "k_solve_grid"),
     ("three-launches-unstaged", {"PTP_FUSED": "0", "PTP_STAGE": "0"}, "k_solve_grid"),
-    ("geometry-table", {"PTP_GEO": "1"}, None),
+    ("geometry-table", {"PTP_GEO": "1", "PTP_GEO_SINGLE": "1"}, None),
     ("no-elastic", {"PTP_ELASTIC": "0"}, None),
 ]
 

@@ -47,3 +47,19 @@ def test_reference_gpu_tool_runs():
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     s = line["solves"][0]
     assert s["gpu_ms"] > 0 and s["max_rel_err_vs_reference_cpu"] < 1e-2
+
+
+def test_report_harness(tmp_path):
+    """gproshan's test_geodesics output for the PTP GPU arm (gproshan_b200/report.py) on two small synthetic meshes"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from gproshan_b200 import meshgen as mg, report
+    s = mg.icosphere(30, dtype=np.float32)
+    g = mg.grid(40)
+    res = report.run([("sphere30", s, report.analytic_exact("sphere", s, 0)), ("grid40", g, report.analytic_exact("plane", g, 0))],
+                     str(tmp_path), n_test=2, fps_counts=(2, 4))
+    assert 0 < res[0]["error_pct"] < 5 and 0 < res[1]["error_pct"] < 5 and res[0]["seconds"] > 0
+    for f in ("ptp_results.tex", "ptp_results_double.tex", "sphere30.deg", "sphere30_toplesets.dist",
+              "sphere30_toplesets_sorted.dist", "sphere30.fps", "grid40.deg"):
+        assert (tmp_path / f).stat().st_size > 0, f
+    assert sum(int(l.split()[1]) for l in open(tmp_path / "sphere30_toplesets.dist")) == s.n_vertices

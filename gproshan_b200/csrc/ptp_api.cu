@@ -39,10 +39,6 @@ int fail(int code, const std::string &msg)
     } while (0)
 
 constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
-#ifndef PTP_MERGED_BLOCK
-#define PTP_MERGED_BLOCK 1024
-#endif
-constexpr int MERGED_BLOCK = PTP_MERGED_BLOCK; // merged single-solve kernel: 1 CTA per SM
 constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
 #ifndef PTP_CLUSTER_BLOCK
 #define PTP_CLUSTER_BLOCK 768 // measured on C3 (f64): 768 threads / 80 registers 27.9 ms, 1024 / 64 29.8, 512 / 128 28.0
@@ -50,7 +46,10 @@ constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (
 constexpr int CLUSTER_BLOCK = PTP_CLUSTER_BLOCK; // cluster single-solve kernel: 1 CTA per SM (BFS cluster + sweep team)
 constexpr int SOLVE_BLOCK = 1024;  // threads per CTA, cooperative sweep kernel (one pass per iteration on C3-size windows)
 template <class R> struct BatchCfg;                    // threads per CTA, one-solve-per-CTA kernels
-template <> struct BatchCfg<float> { static constexpr int BLOCK = 1024; };
+#ifndef PTP_BATCH_BLOCK_F32
+#define PTP_BATCH_BLOCK_F32 1024
+#endif
+template <> struct BatchCfg<float> { static constexpr int BLOCK = PTP_BATCH_BLOCK_F32; };
 template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; };
 constexpr int FLAT_BLOCK = 256;
 #ifndef PTP_GRID_MAP
@@ -281,22 +280,6 @@ __global__ void __launch_bounds__(GRID_BLOCK) k_bfs_grid(MeshView<R> m, Work<R> 
     bfs_run<R, TeamGrid, false>(t, m, w, sources, S, kcap, sent);
 }
 
-// Single solve, one cooperative launch, ONE team running the BFS and the sweep in lock step (PTP_FUSED=3).
-template <class R, bool CL>
-__global__ void __launch_bounds__(MERGED_BLOCK, 1)
-k_geodesics_merged(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged,
-                   u32 bfs_threads)
-{
-    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
-    TeamGrid t{bar, 0, 0, gridDim.x};
-    t.err = w.ctrl + C_ERROR;
-    BfsHook<R, TeamGrid> hook(t, m, w, sent, bfs_threads);
-    hook.b.init(sources, S);
-    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, false, BfsHook<R, TeamGrid>>(
-        t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0, staged ? ptp_dyn_smem : nullptr, &hook);
-    scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
-}
-
 // DEBUG (PTP_FUSED=2): the two halves of the fused kernel as two launches, to time the streamed sweep alone
 template <class R>
 __global__ void __launch_bounds__(FUSED_BLOCK, 2) k_dbg_producer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, u32 sent, ull *bar)
@@ -412,12 +395,12 @@ k_geodesics_fused(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_o
 template <class R, bool CL, bool GEO>
 __global__ void __launch_bounds__(CLUSTER_BLOCK, 1)
 k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 nb,
-                    u32 staged, u32 bfs_flags)
+                    u32 staged)
 {
     extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     if (blockIdx.x < nb) {
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
-        bfs_run_cluster<R, true>(m, w, sources, S, bfs_flags);
+        bfs_run_cluster<R, true>(m, w, sources, S);
         if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
     } else {
         TeamGrid t{bar + 64, 0, nb, gridDim.x - nb};
@@ -430,7 +413,7 @@ k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist
         for (u32 v = tid; v < m.V; v += nth) w.inv[v] = NIL;
         t.sync();
         if (tid == 0) flag_store(w.ctrl + C_FILLED, 1ull);
-        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true, NoHook, GEO>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048,
+        const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true, GEO>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048,
                                                                                m.ring_symmetric != 0, staged ? ptp_dyn_smem : nullptr);
         scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
         if (blockIdx.x == nb && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
@@ -469,8 +452,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         layout_rows_thread<R>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
         __syncthreads();
         const ull t2 = global_timer();
-        const u32 d = ptp_run<R, TeamCta, false, 1, false, NoHook, GEO>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr,
-                                                                       (NoHook *)nullptr, help, counters);
+        const u32 d = ptp_run<R, TeamCta, false, 1, false, GEO>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr, help, counters);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -881,9 +863,7 @@ template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, 
     ull *bar = (ull *)m->w_bar;
     u32 sent = (u32)(m->V + m->ws_scap);
     u32 nb = (u32)csize;
-    static const u32 bfs_flags_env = [] { const char *e = getenv("PTP_BFS_FLAGS"); return e ? (u32)atoi(e) : 0u; }();
-    u32 bfs_flags = bfs_flags_env;
-    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb, &staged, &bfs_flags};
+    void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &nb, &staged};
     CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
@@ -1136,7 +1116,7 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     int rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
-    // PTP_FUSED: 4 (default) cluster BFS + sweep team, 1 two-team kernel, 0 three launches, 2 / 3 debug variants
+    // PTP_FUSED: 4 (default) cluster BFS + sweep team, 1 two-team kernel, 0 three launches, 2 debug (the two teams as two launches)
     static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 4; }();
     if (dbg == 2 && !cl) {
         MeshView<R> mv = mesh_view<R>(m);
@@ -1153,28 +1133,6 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
         CK(cudaEventRecord(m->ev[1], m->stream));
         CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
         CK(cudaLaunchCooperativeKernel((void *)k_dbg_consumer<R>, dim3(m->num_sms), dim3(FUSED_BLOCK), a2, 0, m->stream));
-        CK(cudaEventRecord(m->ev[2], m->stream));
-        return PTP_OK;
-    }
-    if (dbg == 3) {
-        MeshView<R> mv = mesh_view<R>(m);
-        Work<R> w = work_view<R>(m);
-        if (!cl) w.cl[0] = w.cl[1] = nullptr;
-        void *fn = cl ? (void *)k_geodesics_merged<R, true> : (void *)k_geodesics_merged<R, false>;
-        const u32 *src = (const u32 *)m->w_src;
-        R *out = (R *)m->w_out;
-        u32 *clo = (u32 *)m->w_clout;
-        ull *bar = (ull *)m->w_bar;
-        u32 sent = (u32)(m->V + m->ws_scap);
-        u32 staged = use_staging() ? 1u : 0u;
-        const size_t smem = staged ? MERGED_BLOCK * Stage4<R>::bytes_per_thread() : 0;
-        if (staged) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        static const u32 bfs_warps = [] { const char *e = getenv("PTP_BFS_WARPS"); return e ? (u32)atoi(e) : 8u; }();
-        u32 bfs_threads = std::min<u32>(bfs_warps * 32u, MERGED_BLOCK - 64u); // 0 = no warp roles
-        void *args[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged, &bfs_threads};
-        CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
-        CK(cudaLaunchCooperativeKernel(fn, dim3(m->num_sms), dim3(MERGED_BLOCK), args, smem, m->stream));
-        CK(cudaEventRecord(m->ev[1], m->stream));
         CK(cudaEventRecord(m->ev[2], m->stream));
         return PTP_OK;
     }
@@ -1213,9 +1171,7 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
     }
     if ((rc = fetch_ctrl(m))) return rc;
-    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 3)
-        fill_stats(m, st, 1, 0.0, ev_ms(m->ev[0], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
-    else if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
+    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
         fill_stats(m, st, 2, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     else if (use_fused()) {
         // one launch: the producer / consumer split comes from %globaltimer stamps written by the kernel

@@ -370,7 +370,7 @@ def run_single(args, api, torch, peak, peak_src):
         "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
         "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],
         "roofline": {"bound": "hbm", "kernel": kernel + " (BFS team + sweep team, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(kernel.split("<")[0] + "_f64_c3"), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(kernel.split("<")[0] + "_f64_c3") or ncu_traffic("k_geodesics_cluster_f64_c3"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[8],
                      "note": "latency-bound by construction: ~#toplesets dependent iterations (SURVEY.md §0.4)"},
     }

@@ -420,6 +420,41 @@ k_geodesics_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist
     }
 }
 
+// The same two teams as TWO launches that run side by side (PTP_FUSED=5): the BFS needs one cluster, the sweep team
+// needs no clusters at all, and a single cluster launch leaves the SMs that do not fill a GPC's last cluster idle
+// (15 clusters of 8 = 120 of 148 SMs). 8 + 140 CTAs, one per SM; C3: 28.3 -> 24.0 ms.
+template <class R>
+__global__ void __launch_bounds__(CLUSTER_BLOCK, 1) k_toplesets_cluster(MeshView<R> m, Work<R> w, const u32 *sources, u32 S)
+{
+    // programmatic dependent launch: the sweep kernel (next in the stream, launched with programmatic stream
+    // serialisation) may start as soon as every CTA of this grid is resident and has got here — which is exactly the
+    // guarantee needed: the cluster has its eight SMs of one GPC before the sweep CTAs take whatever is left
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TSTART] = global_timer();
+    bfs_run_cluster<R, true>(m, w, sources, S);
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TBFS] = global_timer();
+}
+
+template <class R, bool CL, bool GEO>
+__global__ void __launch_bounds__(CLUSTER_BLOCK, 1)
+k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar)
+{
+    TeamGrid t{bar + 64, 0, 0, gridDim.x};
+    t.err = w.ctrl + C_ERROR;
+    const u32 tid = t.cta() * blockDim.x + threadIdx.x, nth = t.nctas() * blockDim.x;
+    uint4 *key4 = reinterpret_cast<uint4 *>(w.key);
+    const uint4 ones = make_uint4(NIL, NIL, NIL, NIL);
+    for (u32 i = tid; i < m.V / 2; i += nth) key4[i] = ones;
+    if (tid == 0 && (m.V & 1u)) w.key[m.V - 1] = ~0ull;
+    for (u32 v = tid; v < m.V; v += nth) w.inv[v] = NIL;
+    t.sync();
+    if (tid == 0) flag_store(w.ctrl + C_FILLED, 1ull);
+    const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true, GEO>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
+                                                                   nullptr);
+    scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
+}
+
 // one CTA per solve, CTAs pull source sets from a queue
 template <class R, bool GEO>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
@@ -525,6 +560,8 @@ struct ptp_mesh {
     u64 ovf_total = 0;
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
     bool geo_failed = false; // the table did not fit: do not try again
+    bool two_failed = false; // the two-launch single solve did not get both kernels resident once: use one launch from now on
+    bool last_two = false;   // the last single solve ran as two launches
     const char *last_kernel = ""; // dominant kernel of the last call on this mesh (ptp_mesh_last_kernel)
     u64 bytes = 0;
     cudaStream_t stream = nullptr;
@@ -877,6 +914,69 @@ template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, 
     return PTP_OK;
 }
 
+// PTP_FUSED=5: BFS cluster kernel + sweep kernel side by side (see k_toplesets_cluster): same stream, the second one a
+// programmatic dependent of the first, so that it starts once the BFS cluster is resident instead of when it has finished.
+template <class R> int launch_two_kernels(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, bool *launched)
+{
+    *launched = false;
+    m->last_two = false;
+    const int csize = cluster_size();
+    if (m->two_failed || m->num_sms < csize + 32) return PTP_OK;
+    MeshView<R> mv = mesh_view<R>(m);
+    mv.geo = nullptr;
+    Work<R> w = work_view<R>(m);
+    if (!cl) w.cl[0] = w.cl[1] = nullptr;
+    const u32 *src = (const u32 *)m->w_src;
+    R *out = (R *)m->w_out;
+    u32 *clo = (u32 *)m->w_clout;
+    ull *bar = (ull *)m->w_bar;
+    u32 sent = (u32)(m->V + m->ws_scap);
+    void *fb = (void *)k_toplesets_cluster<R>;
+    void *fs = cl ? (void *)k_sweep_streamed<R, true, false> : (void *)k_sweep_streamed<R, false, false>;
+    if (csize > 8 && cudaFuncSetAttribute(fb, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return PTP_OK;
+    }
+    // both kernels must be loaded before either runs: with lazy module loading the first launch of the second one would
+    // otherwise wait for the device to drain, i.e. for the first one, which is waiting for it
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, fb));
+    CK(cudaFuncGetAttributes(&fa, fs));
+    CK(cudaMemsetAsync(m->w_bar, 0, 1024, m->stream));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csize;
+    at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)csize);
+    cfg.blockDim = dim3(CLUSTER_BLOCK);
+    cfg.stream = m->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void *a1[] = {&mv, &w, &src, &S};
+    if (cudaLaunchKernelExC(&cfg, fb, a1) != cudaSuccess) {
+        cudaGetLastError();
+        return PTP_OK;
+    }
+    // (a plain launch, not a cooperative one: that would be held back until the device is idle; with one CTA per
+    // remaining SM every CTA is resident, and the watchdog covers the rest)
+    cudaLaunchConfig_t cfg2 = {};
+    cudaLaunchAttribute at2[1];
+    at2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at2[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg2.gridDim = dim3((unsigned)(m->num_sms - csize));
+    cfg2.blockDim = dim3(CLUSTER_BLOCK);
+    cfg2.stream = m->stream;
+    cfg2.attrs = at2;
+    cfg2.numAttrs = 1;
+    void *a2[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar};
+    CK(cudaLaunchKernelExC(&cfg2, fs, a2));
+    m->last_kernel = sizeof(R) == 8 ? "k_sweep_streamed<double> + k_toplesets_cluster<double>" : "k_sweep_streamed<float> + k_toplesets_cluster<float>";
+    m->last_two = true;
+    *launched = true;
+    return PTP_OK;
+}
+
 void fill_stats(const ptp_mesh *m, ptp_stats_t *st, u64 launches, double ms_top, double ms_solve, double ms_total)
 {
     if (!st) return;
@@ -1116,8 +1216,9 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
     int rc;
     CK(cudaEventRecord(m->ev[0], m->stream));
-    // PTP_FUSED: 4 (default) cluster BFS + sweep team, 1 two-team kernel, 0 three launches, 2 debug (the two teams as two launches)
-    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 4; }();
+    // PTP_FUSED: 5 (default) BFS cluster kernel + sweep kernel side by side, 4 the same two teams in ONE cluster launch,
+    // 1 two-team kernel (grid barriers only), 0 three launches, 2 debug (the two teams one after the other)
+    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 5; }();
     if (dbg == 2 && !cl) {
         MeshView<R> mv = mesh_view<R>(m);
         Work<R> w = work_view<R>(m);
@@ -1138,7 +1239,9 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     }
     if (use_fused()) {
         bool launched = false;
-        if (dbg != 1 && (rc = launch_cluster<R>(m, S, cl, cl_fill, &launched))) return rc; // PTP_FUSED=1: the two-team kernel
+        m->last_two = false;
+        if (dbg >= 5 && (rc = launch_two_kernels<R>(m, S, cl, cl_fill, &launched))) return rc;
+        if (!launched && dbg != 1 && (rc = launch_cluster<R>(m, S, cl, cl_fill, &launched))) return rc; // PTP_FUSED=1: the two-team kernel
         if (!launched && (rc = launch_fused<R>(m, S, cl, cl_fill))) return rc;
         CK(cudaEventRecord(m->ev[1], m->stream));
         CK(cudaEventRecord(m->ev[2], m->stream));
@@ -1161,16 +1264,25 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
     if ((rc = check_sources(m, sources, S))) return rc;
     if (!dist) return fail(PTP_ERR_INVALID, "dist is null");
     if ((rc = ensure_workspace<R>(m, S, clusters != nullptr, false))) return rc;
-    if ((rc = upload_sources<R>(m, sources, S))) return rc;
-    if ((rc = pipeline<R>(m, S, clusters != nullptr, cl_fill))) return rc;
-    CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
-    if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
-    if (sorted_index) {
-        // p is only known on the device; copy what the caller can hold and validate afterwards
-        const u64 n = std::min<u64>(scap, m->V + S);
-        CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
+    for (int attempt = 0;; attempt++) {
+        if ((rc = upload_sources<R>(m, sources, S))) return rc;
+        if ((rc = pipeline<R>(m, S, clusters != nullptr, cl_fill))) return rc;
+        CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
+        if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
+        if (sorted_index) {
+            // p is only known on the device; copy what the caller can hold and validate afterwards
+            const u64 n = std::min<u64>(scap, m->V + S);
+            CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
+        }
+        rc = fetch_ctrl(m);
+        if (rc && m->last_two && attempt == 0 && ((const ull *)m->h_ctrl)[C_ERROR]) {
+            // the two kernels did not become resident together (the watchdog ended them): one launch from now on
+            m->two_failed = true;
+            continue;
+        }
+        if (rc) return rc;
+        break;
     }
-    if ((rc = fetch_ctrl(m))) return rc;
     if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
         fill_stats(m, st, 2, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     else if (use_fused()) {
@@ -1196,7 +1308,7 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
                 fprintf(stderr, "[ptp] cluster BFS thread-0 ms: claim %.2f | barrier1 %.2f | publish %.2f | own+scan %.2f | barrier2 %.2f | place+barrier3 %.2f\n",
                         c[C_TPHASE] * 1e-6, c[C_TPHASE + 1] * 1e-6, c[C_TPHASE + 5] * 1e-6, c[C_TPHASE + 2] * 1e-6, c[C_TPHASE + 3] * 1e-6, c[C_TPHASE + 4] * 1e-6);
         }
-        fill_stats(m, st, 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
+        fill_stats(m, st, m->last_two ? 2 : 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
     } else
         fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     if (sorted_index && scap < ((const ull *)m->h_ctrl)[C_REACHED])

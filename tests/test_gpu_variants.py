@@ -12,9 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 VARIANTS = [
-    ("default", {}, "k_geodesics_cluster"),
+    ("default", {}, "k_sweep_streamed"),
+    ("one-cluster-launch", {"PTP_FUSED": "4"}, "k_geodesics_cluster"),
     ("cluster-16", {"PTP_CLUSTER": "16"}, None),           # non-portable cluster size: may fall back, must stay correct
-    ("cluster-staged", {"PTP_STAGE": "1"}, None),
+    ("cluster-staged", {"PTP_FUSED": "4", "PTP_STAGE": "1"}, None),
     ("two-team", {"PTP_FUSED": "1"}, "k_geodesics_fused"),
     ("two-team-staged", {"PTP_FUSED": "1", "PTP_STAGE": "2"}, "k_geodesics_fused"),
     ("three-launches", {"PTP_FUSED": "0"}, "k_solve_grid"),

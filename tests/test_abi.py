@@ -44,3 +44,23 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_lib" not in src and "libptp_oracle" not in src and "orc_" not in src, f
+
+
+def test_reference_gpu_leg_degrades_without_a_gpu():
+    """bench.py's second-baseline leg (the reference's own CUDA PTP, run in a subprocess) must never take the bench line
+    down: without a GPU (or without the reference build) it reports `unavailable`."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("a GPU is present: the leg would run")
+    except ImportError:
+        pass
+    r = bench.reference_gpu_leg("c3", True, 1, False)
+    assert isinstance(r, dict) and "unavailable" in r

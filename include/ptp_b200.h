@@ -53,7 +53,7 @@ typedef struct ptp_stats {
     uint64_t gpu_launches;   /* kernels this call launched                                            */
     double ms_toplesets;     /* BFS + topleset-order layout (batched: mean per-CTA time over the launch)  */
     double ms_solve;         /* relaxation sweep + scatter back to vertex order (batched: mean per CTA;   *
-                              * fused single solve: start of kernel to end of sweep team)                 */
+                              * single solve with device toplesets: start of the BFS kernel to end of sweep team) */
     double ms_total;         /* first launch to last launch, device time (CUDA events)                */
 } ptp_stats_t;
 

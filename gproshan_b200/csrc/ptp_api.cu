@@ -970,7 +970,15 @@ template <class R> int launch_two_kernels(ptp_mesh *m, u32 S, bool cl, u32 cl_fi
     cfg2.attrs = at2;
     cfg2.numAttrs = 1;
     void *a2[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar};
-    CK(cudaLaunchKernelExC(&cfg2, fs, a2));
+    if (cudaLaunchKernelExC(&cfg2, fs, a2) != cudaSuccess) {
+        // the dependent launch was refused: the BFS kernel already in the stream gives up through its watchdog; start
+        // over with a clean control block and let the caller use the one-launch kernel, now and from now on
+        cudaGetLastError();
+        m->two_failed = true;
+        CK(cudaStreamSynchronize(m->stream));
+        CK(cudaMemsetAsync(m->w_ctrl, 0, 8 * C_COUNT, m->stream));
+        return PTP_OK;
+    }
     m->last_kernel = sizeof(R) == 8 ? "k_sweep_streamed<double> + k_toplesets_cluster<double>" : "k_sweep_streamed<float> + k_toplesets_cluster<float>";
     m->last_two = true;
     *launched = true;

@@ -6,13 +6,13 @@
     torchrun ... bench.py --gpus N ...                        # one process per GPU (batched sources sharded)
 
 Workloads (BASELINE.json configs):
-  batched  C5: icosphere f=447 (1 998 092 vertices, float), independent single-source solves, 128 sources per
-           GPU (weak scaling: N=8 is the 1024-source distance-matrix job), rows gathered with one NCCL all_gather.
-           This is the line's `metric`/`value` at every N so the driver's scaling numbers compare like with like.
+  batched  C5: icosphere f=447 (1 998 092 vertices, float), the 1024 independent single-source solves of the
+           distance-matrix job at EVERY N: 1024 / N sources per GPU (strong scaling), rows gathered with NCCL to the
+           full 1024 x V matrix. This is the line's `metric` / `value`.
   single   C3: noisy icosphere f=1000 (10 000 002 vertices, double), one source; reported on the N=1 line under
            "single_source" (ms/solve, vertex-updates/s, its own roofline, e2e and CPU baseline).
 
-A step = one pass of the hot path: one batched call over this rank's sources (+ gather), or one solve.
+A step = one pass of the hot path over the whole job: one batched call over this rank's sources + the gather.
 """
 from __future__ import annotations
 
@@ -38,11 +38,34 @@ def log(*a):
 
 
 def ncu_traffic(kernel_key):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-    (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from THIS round's
+    `ncu --set full` capture of the same workload (profiles/r2_traffic.json: {key: {"bytes": .., "commit": ..,
+    "command": ..}}, written by tools/ncu_traffic.py); None when the kernel has not been captured this round."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        return json.load(open(p)).get(kernel_key)
+        e = json.load(open(p)).get(kernel_key)
+        return e if e is None else e["bytes"]
+    except Exception:
+        return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pin_openmp(n):
+    """The CPU arms run the reference's OpenMP code on ALL host threads, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 for its workers). The variable covers libgomp instances not loaded yet, omp_set_num_threads the
+    one already in the process. -> omp_get_max_threads() as seen afterwards."""
+    import ctypes
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        g = ctypes.CDLL("libgomp.so.1")
+        g.omp_set_num_threads(int(n))
+        return int(g.omp_get_max_threads())
     except Exception:
         return None
 
@@ -148,14 +171,27 @@ def cpu_runner(dtype):
 
 
 def cpu_sources_per_s(mesh, srcs, budget_s, max_n):
+    """-> (kind, rows solved on the CPU (list of arrays), seconds)"""
     kind, make = cpu_runner(mesh.GT.dtype)
     solve = make(mesh)
-    n, t0 = 0, time.perf_counter()
-    while n < max_n and (n == 0 or time.perf_counter() - t0 < budget_s):
-        solve(srcs[n:n + 1])
-        n += 1
+    rows, t0 = [], time.perf_counter()
+    while len(rows) < max_n and (not rows or time.perf_counter() - t0 < budget_s):
+        rows.append(solve(srcs[len(rows):len(rows) + 1])[0])
     dt = time.perf_counter() - t0
-    return kind, n, dt
+    return kind, rows, dt
+
+
+N_SOURCES = 1024  # BASELINE.json config 5: the distance-matrix job
+
+
+def c5_config(wl, world):
+    """The line's `config`: identical for both arms (the reference arm times a bounded sample of the same job)."""
+    per = N_SOURCES // world
+    return {"workload": wl, "sources_total": per * world, "sources_per_gpu": per, "gpus": world,
+            "sharding": ("sources block-partitioned over the GPUs, mesh replicated, rows gathered with NCCL (all_gather) into the "
+                         "full matrix on every GPU" if world > 1 else "single GPU"),
+            "l2": "inputs larger than L2: per step 1024 x V distance rows (8.2 GB) are produced and every solve rebuilds its "
+                  "own workspace; no explicit flush"}
 
 
 def reference_gpu_leg(workload, quick, sources, coalescence):
@@ -180,10 +216,12 @@ def reference_gpu_leg(workload, quick, sources, coalescence):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU PTP (compute_toplesets + parallel_toplesets_propagation_cpu) on the
-    host cores, same config and metric. Rank 0 only."""
+    host cores, same config and metric; each step is a bounded sample (`--ref-sources-per-step` sources) of the job.
+    Rank 0 only; the OpenMP thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_threads()
+    omp = pin_openmp(cores)
     mesh, srcs, wl = build_c5(args.quick)
     kind, make = cpu_runner(mesh.GT.dtype)
     solve = make(mesh)
@@ -204,10 +242,11 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "ptp_batched_sources_per_s", "value": val, "unit": "sources/s", "n_gpus": args.gpus,
         "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps_done, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "sources_per_step": per_step, "note": "CPU PTP on host cores; a step is a bounded sample of the batch"},
-        "cpu_baseline": {"value": val, "unit": "sources/s", "cores": cores, "kind": kind,
-                         "sample": f"{done} single-source solves (compute_toplesets + parallel_toplesets_propagation_cpu), OpenMP on {cores} threads"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": c5_config(wl, max(1, args.gpus)),
+        "cpu_baseline": {"value": val, "unit": "sources/s", "cores": omp or cores, "kind": kind,
+                         "sample": f"{done} of the {N_SOURCES} single-source solves ({per_step} per step; compute_toplesets + "
+                                   f"parallel_toplesets_propagation_cpu), OpenMP: omp_get_max_threads() = {omp} on {cores} host threads"},
         "e2e": {"value": val, "unit": "sources/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -227,18 +266,19 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peak, peak_src = measured_peaks()
 
-    # ---------------- batched (the line's metric)
+    # ---------------- batched (the line's metric): the whole 1024-source job at every N
     mesh, srcs_all, wl = build_c5(args.quick)
     V = mesh.n_vertices
     from gproshan_b200.sharding import gather_rows, shard_sources
-    per_gpu = min(args.batch_per_gpu, srcs_all.size // world)
-    mine = np.ascontiguousarray(shard_sources(srcs_all, rank, world, per_rank=per_gpu))
+    n_total = min(args.sources, srcs_all.size) // world * world
+    per_gpu = n_total // world
+    mine = np.ascontiguousarray(shard_sources(srcs_all[:n_total], rank, world, per_rank=per_gpu))
     t = time.perf_counter()
     dm = api.DeviceMesh(mesh, device=local_rank)
     torch.cuda.synchronize()
     upload_s = time.perf_counter() - t
     rows = torch.empty((per_gpu, V), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((per_gpu * world, V), dtype=torch.float32, device="cuda") if world > 1 else None
+    gathered = torch.empty((n_total, V), dtype=torch.float32, device="cuda") if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_resident():
@@ -273,56 +313,87 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(upd, op=dist.ReduceOp.SUM)
     ms_total = float(ms.item())
     ms_step = ms_total / args.steps
-    value = per_gpu * world / (ms_step / 1e3)
+    value = n_total / (ms_step / 1e3)
 
-    # e2e: host sources in, host rows out (pinned), every step
-    host_rows = torch.empty((per_gpu, V), dtype=torch.float32, pin_memory=True)
-    host_np = host_rows.numpy()
+    # e2e: host sources in, the assembled n_total x V matrix out in pinned HOST memory, every step.
+    #   N = 1: the C-ABI call with host pointers (H2D of the sources, D2H of the rows inside the call).
+    #   N > 1: every rank solves its shard (sources from the host), the rows are gathered with NCCL and rank 0 copies the
+    #          assembled matrix to its pinned host buffer: the step ends when that copy has landed.
     e2e_steps = max(1, min(args.steps, 3))
-    dm.solve_batched(mine, rows=host_np)
+    host_rows = torch.empty((n_total, V), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+
+    def step_e2e():
+        if world == 1:
+            dm.solve_batched(mine, rows=host_rows.numpy())
+        else:
+            dm.solve_batched(mine, rows_device_ptr=rows.data_ptr(), stream=stream)
+            gather_rows(rows, world, out=gathered)
+            if rank == 0:
+                host_rows.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize()
+        return float(host_rows[0, :8].sum()) if rank == 0 else 0.0
+
+    step_e2e()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     t = time.perf_counter()
     for _ in range(e2e_steps):
-        dm.solve_batched(mine, rows=host_np)
-        checksum = float(host_np[0, :8].sum())
+        checksum = step_e2e()
+        if dist:
+            dist.barrier()
     e2e_s = torch.tensor([time.perf_counter() - t], device="cuda")
     if dist:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = per_gpu * world * e2e_steps / float(e2e_s.item())
+    e2e_val = n_total * e2e_steps / float(e2e_s.item())
 
     kernel_ms = statistics.mean(kern_ms)
+    kernel = dm.last_kernel
     achieved = updates * BYTES_PER_UPDATE[4] / (kernel_ms / 1e3) / 1e9
     line = {
         "metric": "ptp_batched_sources_per_s", "value": value, "unit": "sources/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl, "sources_per_gpu": per_gpu, "sources_total": per_gpu * world,
-                   "sharding": "sources block-partitioned, mesh replicated, one NCCL all_gather of the rows" if world > 1 else "single GPU",
-                   "l2": "per-solve working set ~150 MB x resident solves exceeds the 126 MB L2; no explicit flush",
-                   "vertex_updates_per_step_all_gpus": float(upd.item()), "mesh_upload_s": upload_s},
+        "config": c5_config(wl, world) if n_total == N_SOURCES else dict(c5_config(wl, world), sources_total=n_total, sources_per_gpu=per_gpu),
+        "vertex_updates_per_step_all_gpus": float(upd.item()), "mesh_upload_s": upload_s,
         "vertex_updates_per_s": float(upd.item()) / (ms_step / 1e3),
-        "e2e": {"value": e2e_val, "unit": "sources/s", "h2d_bytes_per_step": int(mine.nbytes),
-                "d2h_bytes_per_step": int(host_np.nbytes), "steps": e2e_steps, "checksum": checksum},
+        "e2e": {"value": e2e_val, "unit": "sources/s", "h2d_bytes_per_step": int(mine.nbytes) * world,
+                "d2h_bytes_per_step": int(n_total) * V * 4, "steps": e2e_steps, "checksum": checksum,
+                "what": ("C-ABI call, host sources in, pinned host rows out" if world == 1 else
+                         "per rank: host sources in, rows on device; NCCL all_gather; rank 0 copies the assembled matrix to pinned host memory")},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_batched<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic("k_batched_f32_c5_128"), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic("c5_batched_f32"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[4], "vertex_updates_per_launch": updates,
                      "achieved_counting_executed_relaxations_only": st["relaxations"] * BYTES_PER_UPDATE[4] / (kernel_ms / 1e3) / 1e9,
                      "relaxations_per_launch": st["relaxations"], "kernel_ms": kernel_ms,
-                     "note": "rank 0's kernel; includes BFS + layout + sweep of every source in the launch. vertex_updates = the "
-                             "reference schedule's window sizes (skipped relaxations included); the kernel is FP32-issue "
-                             "bound, not HBM bound (profiles/)"},
+                     "note": "rank 0's launch (its share of the job); includes BFS + layout + sweep of every source in the launch. "
+                             "vertex_updates = the reference schedule's window sizes (skipped relaxations included)"},
         "clocks": clocks,
     }
 
-    if rank == 0 and world == 1 and args.workload in ("auto", "both", "single"):
-        line["single_source"] = run_single(args, api, torch, peak, peak_src)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        kind, n, dt = cpu_sources_per_s(mesh, mine, args.cpu_budget_s, 16)
-        line["cpu_baseline"] = {"value": n / dt, "unit": "sources/s", "cores": os.cpu_count(), "kind": kind,
-                                "sample": f"{n} of the {per_gpu} sources of this workload, {dt:.1f}s, OpenMP on all host threads"}
+        # the reference's CPU PTP on a bounded sample of the SAME sources; its rows are the parity check of the GPU rows
+        cores = host_threads()
+        omp = pin_openmp(cores)
+        kind, cpu_rows, dt = cpu_sources_per_s(mesh, mine, args.cpu_budget_s, 16)
+        n = len(cpu_rows)
+        got = rows[:n].cpu().numpy()
+        worst, equal = 0.0, True
+        for k in range(n):
+            fin = np.isfinite(cpu_rows[k])
+            equal = equal and bool(np.array_equal(got[k], cpu_rows[k]))
+            if fin.any():
+                worst = max(worst, float((np.abs(got[k][fin] - cpu_rows[k][fin]) / np.maximum(cpu_rows[k][fin], 1e-30)).max()))
+        line["cpu_baseline"] = {"value": n / dt, "unit": "sources/s", "cores": omp or cores, "kind": kind,
+                                "sample": f"{n} of the {n_total} sources of this workload, {dt:.1f}s, OpenMP: omp_get_max_threads() = {omp}"}
+        line["parity"] = {"rows_checked": n, "bit_equal": equal, "max_rel_err": worst, "tolerance": 1e-5,
+                          "against": "the reference's CPU PTP (oracle/_ref) on the same sources" if kind == "reference" else "the oracle port"}
+    del rows, gathered, host_rows
+    if rank == 0 and world == 1 and args.workload in ("auto", "both", "single"):
+        dm.close()
+        torch.cuda.empty_cache()
+        line["single_source"] = run_single(args, api, torch, peak, peak_src)
     dm.close()
     if rank == 0 and world == 1 and not args.no_ref_gpu:
         torch.cuda.synchronize()
@@ -370,18 +441,19 @@ def run_single(args, api, torch, peak, peak_src):
         "e2e": {"ms_per_solve": statistics.median(wall), "h2d_bytes": 4, "d2h_bytes": int(out.nbytes)},
         "mesh_upload_s": upload_s, "steps": steps, "gpu_launches_per_solve": st["gpu_launches"],
         "roofline": {"bound": "hbm", "kernel": kernel + " (BFS team + sweep team, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(kernel.split("<")[0] + "_f64_c3") or ncu_traffic("k_geodesics_cluster_f64_c3"), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic("c3_single_f64"), "peak_source": peak_src,
                      "algorithmic_bytes_per_vertex_update": BYTES_PER_UPDATE[8],
                      "note": "latency-bound by construction: ~#toplesets dependent iterations (SURVEY.md §0.4)"},
     }
     if not args.no_cpu_baseline:
+        omp = pin_openmp(host_threads())
         kind, make = cpu_runner(np.float64)
         solve = make(mesh)
         t = time.perf_counter()
         ref, lim, srt = solve(src)
         cpu_s = time.perf_counter() - t
         rel = np.abs(out - ref)[np.isfinite(ref)] / np.maximum(ref[np.isfinite(ref)], 1e-300)
-        res["cpu_baseline"] = {"value": cpu_s * 1e3, "unit": "ms/solve", "cores": os.cpu_count(), "kind": kind,
+        res["cpu_baseline"] = {"value": cpu_s * 1e3, "unit": "ms/solve", "cores": omp or host_threads(), "kind": kind,
                                "sample": "1 full solve (compute_toplesets + parallel_toplesets_propagation_cpu)"}
         res["parity_vs_cpu"] = {"max_rel_err": float(rel.max()), "bit_equal": bool(np.array_equal(out, ref))}
     dm.close()
@@ -395,7 +467,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "single", "batched", "both"])
-    ap.add_argument("--batch-per-gpu", type=int, default=128)
+    ap.add_argument("--sources", type=int, default=N_SOURCES, help="sources of the batched job (default: the full 1024)")
     ap.add_argument("--quick", action="store_true", help="small meshes (smoke / CI)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own CUDA PTP (second baseline)")

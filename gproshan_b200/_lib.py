@@ -33,6 +33,8 @@ class Stats(C.Structure):
 # every symbol include/ptp_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "ptp_last_error", "ptp_device_count", "ptp_version", "ptp_host_alloc", "ptp_host_free",
+    "ptp_set_option", "ptp_get_option", "ptp_option_name", "ptp_option_doc",
+    "ptp_mesh_update_positions_f32", "ptp_mesh_update_positions_f64",
     "ptp_mesh_create_f32", "ptp_mesh_create_f64", "ptp_mesh_destroy", "ptp_mesh_last_kernel", "ptp_che_build", "ptp_mesh_n_vertices",
     "ptp_mesh_n_half_edges", "ptp_mesh_real_size", "ptp_mesh_device", "ptp_mesh_device_bytes",
     "ptp_toplesets", "ptp_solve_f32", "ptp_solve_f64", "ptp_geodesics_f32", "ptp_geodesics_f64",
@@ -60,8 +62,15 @@ def lib():
     L.ptp_host_alloc.argtypes = [C.c_size_t]
     L.ptp_host_free.argtypes = [vp]
     L.ptp_host_free.restype = None
+    L.ptp_set_option.argtypes = [C.c_char_p, C.c_long]
+    L.ptp_get_option.argtypes = [C.c_char_p]
+    L.ptp_get_option.restype = C.c_long
+    for n in ("ptp_option_name", "ptp_option_doc"):
+        getattr(L, n).argtypes = [C.c_int]
+        getattr(L, n).restype = C.c_char_p
     for suf, ct in (("f32", C.c_float), ("f64", C.c_double)):
         rp = C.POINTER(ct)
+        getattr(L, f"ptp_mesh_update_positions_{suf}").argtypes = [vp, rp]
         f = getattr(L, f"ptp_mesh_create_{suf}")
         f.argtypes = [rp, u32p, u32p, u32p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp)]
         f = getattr(L, f"ptp_solve_{suf}")

@@ -39,6 +39,24 @@ def device_count() -> int:
     return _lib.lib().ptp_device_count()
 
 
+def set_option(name: str, value: int) -> None:
+    """ptp_set_option: kernel-variant switches of the library (see `options()`); same bits whatever the choice."""
+    check(_lib.lib().ptp_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    return _lib.lib().ptp_get_option(name.encode())
+
+
+def options() -> dict:
+    """{name: (value, doc)} of every switch the library has."""
+    L, out, i = _lib.lib(), {}, 0
+    while (n := L.ptp_option_name(i)) is not None:
+        out[n.decode()] = (L.ptp_get_option(n), L.ptp_option_doc(i).decode())
+        i += 1
+    return out
+
+
 def che_build(faces, n_vertices: int, device: int = 0):
     """OT / EVT from a face list on the GPU (che::update_evt_ot_et, src/che.cpp:1295-1362).
     -> (OT, EVT, manifold, device_ms)"""
@@ -95,6 +113,12 @@ class DeviceMesh:
 
     def __exit__(self, *a):
         self.close()
+
+    def update_positions(self, xyz):
+        """new vertex positions, same connectivity (ptp_mesh_update_positions_*)"""
+        GT = np.ascontiguousarray(xyz, dtype=self.dtype)
+        assert GT.shape == (self.n_vertices, 3)
+        check(getattr(_lib.lib(), f"ptp_mesh_update_positions_{self.suf}")(self._h, _p(GT, self.ct)))
 
     @property
     def last_kernel(self) -> str:

@@ -4,10 +4,12 @@
 #include "ptp_device.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -38,6 +40,51 @@ int fail(int code, const std::string &msg)
         }                                                                                                     \
     } while (0)
 
+// Behaviour switches (ptp_set_option / ptp_get_option, include/ptp_b200.h). Each starts from the environment variable
+// PTP_<NAME IN CAPITALS> when it is set (read once, at the first use of the library) and can be changed at any time
+// through the API; the library never calls getenv() anywhere else.
+struct Option { const char *name; long value; const char *doc; };
+Option g_options[] = {
+    {"fused", 5, "single solve: 5 BFS-cluster kernel + sweep kernel side by side (falls back to 4), 4 the same two teams in one "
+                 "cluster launch, 1 two-team kernel with grid barriers, 0 three launches, 2 debug (the teams one after the other)"},
+    {"stage", -1, "window staged in shared memory: -1 per-variant default (on for the three-launch sweep only), 0 off, "
+                  "1 also in the cluster kernel, 2 also in the two-team kernel"},
+    {"bfs_ctas", 0, "CTAs of the BFS team in the two-team kernel (0 = one per SM)"},
+    {"cluster", 8, "CTAs of the BFS thread-block cluster (<= 8 portable, <= 16 non-portable)"},
+    {"geo_single", 0, "single solve reads the per-mesh geometry table"},
+    {"geo", 0, "batched solves read the per-mesh geometry table"},
+    {"elastic", 1, "one-CTA-per-solve batched kernel: idle CTAs execute ticketed chunks of running solves"},
+    {"causal", 1, "batched solves skip triangles that provably cannot lower a vertex (both neighbours above it; bit-exact)"},
+    {"team", 0, "batched solves: CTAs per solve (0 = default for the mesh size, 1 = one CTA per solve)"},
+    {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
+                  "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
+    {"profile_range", 0, "bracket every single solve with cudaProfilerStart/Stop (ncu --replay-mode range / app-range)"},
+    {"debug", 0, "print per-phase device timers to stderr"},
+};
+constexpr int N_OPTIONS = (int)(sizeof g_options / sizeof g_options[0]);
+std::mutex g_opt_mu;
+
+void options_init()
+{
+    static bool done = [] {
+        for (Option &o : g_options) {
+            std::string env = "PTP_";
+            for (const char *c = o.name; *c; c++) env += (char)toupper((unsigned char)*c);
+            if (const char *e = getenv(env.c_str())) o.value = atol(e);
+        }
+        return true;
+    }();
+    (void)done;
+}
+
+long opt(const char *name)
+{
+    options_init();
+    for (const Option &o : g_options)
+        if (!strcmp(o.name, name)) return o.value;
+    return 0;
+}
+
 constexpr int GRID_BLOCK = 512;    // threads per CTA, cooperative BFS kernel
 constexpr int FUSED_BLOCK = 512;   // fused single-solve kernel: 2 CTAs per SM (one BFS-team CTA + one sweep-team CTA)
 #ifndef PTP_CLUSTER_BLOCK
@@ -49,8 +96,11 @@ template <class R> struct BatchCfg;                    // threads per CTA, one-s
 #ifndef PTP_BATCH_BLOCK_F32
 #define PTP_BATCH_BLOCK_F32 1024
 #endif
-template <> struct BatchCfg<float> { static constexpr int BLOCK = PTP_BATCH_BLOCK_F32; };
-template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; };
+#ifndef PTP_BATCH_MINBLOCKS_F32
+#define PTP_BATCH_MINBLOCKS_F32 1
+#endif
+template <> struct BatchCfg<float> { static constexpr int BLOCK = PTP_BATCH_BLOCK_F32; static constexpr int MINB = PTP_BATCH_MINBLOCKS_F32; };
+template <> struct BatchCfg<double> { static constexpr int BLOCK = 512; static constexpr int MINB = 1; };
 constexpr int FLAT_BLOCK = 256;
 #ifndef PTP_GRID_MAP
 #define PTP_GRID_MAP 4 // lanes per vertex in the whole-GPU sweep: 8 (one triangle per lane) or 4 (two per lane)
@@ -204,6 +254,40 @@ __global__ void k_geo_build(const typename Ops<R>::vec4 *__restrict__ GT4, const
     }
 }
 
+// Causal-safe flags (MeshView::safe8): bit k of safe8[v] = the planar update on triangle k = (v, n_k, n_{k+1}) obeys the
+// bound p >= min(t0, t1)(1 - 75 u) (causal_safe in ptp_device.cuh). One thread per vertex; overflow rows get 0.
+template <class R>
+__global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, const u32 *__restrict__ ring8, u32 V, unsigned char *__restrict__ safe8)
+{
+    typedef Ops<R> O;
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const u32 *row = ring8 + (size_t)v * GL;
+    u32 e[GL];
+    for (u32 k = 0; k < GL; k++) e[k] = row[k];
+    u32 len = 0, bits = 0;
+    bool open = false;
+    if (e[0] != OVF && e[0] != NIL) {
+        open = (e[0] & OPEN_BIT) != 0;
+        e[0] &= ~OPEN_BIT;
+        while (len < GL && e[len] != NIL) len++;
+    }
+    const u32 n_tri = len == 0 ? 0 : (open ? len - 1 : len);
+    const P3<R> Ps = load_pos<R>(GT4 + v);
+    P3<R> X[GL];
+    R q[GL];
+    for (u32 k = 0; k < len; k++) {
+        const P3<R> Pn = load_pos<R>(GT4 + e[k]);
+        X[k] = {O::sub(Pn.x, Ps.x), O::sub(Pn.y, Ps.y), O::sub(Pn.z, Ps.z)};
+        q[k] = dot3(X[k], X[k]);
+    }
+    for (u32 k = 0; k < n_tri; k++) {
+        const u32 k1 = k + 1 < len ? k + 1 : 0;
+        if (causal_safe<R>(X[k], X[k1], q[k], q[k1])) bits |= 1u << k;
+    }
+    safe8[v] = (unsigned char)bits;
+}
+
 // ------------------------------------------------------------------------------------------------
 // CHE construction on the device (reference: che::update_evt_ot_et, src/che.cpp:1295-1362, serial, ~22 s at
 // 10 M vertices). Directed edges (a -> b) go into an open-addressing hash table keyed by (a << 32 | b);
@@ -342,6 +426,7 @@ template <class R> __global__ void k_inv_fill(MeshView<R> m, Work<R> w, u32 p)
     if (r < p) {
         const u32 v = w.sorted[r];
         if (v < m.V) atomicMin(&w.inv[v], r);
+        else atomicAdd(w.ctrl + C_ABORT, 1ull); // out-of-range entry: reported by the host before anything uses the table
     }
 }
 
@@ -456,14 +541,18 @@ k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_ou
 }
 
 // one CTA per solve, CTAs pull source sets from a queue
-template <class R, bool GEO>
-__global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
+template <class R, bool GEO, bool CAUSAL>
+__global__ void __launch_bounds__(BatchCfg<R>::BLOCK, BatchCfg<R>::MINB)
 k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
-          ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */)
+          ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */, u32 n_slots)
 {
     __shared__ u32 s_b;
     __shared__ u32 s_wl[2];
     TeamCta t;
+    if (blockIdx.x >= n_slots) { // a CTA without a workspace of its own (more CTAs than slots): helper from the start
+        if (descs) help_loop<R, GEO, CAUSAL>(m.geo, works, descs, n_slots, counters, counters + 1, B);
+        return;
+    }
     const Work<R> w = works[blockIdx.x];
     HelpDesc *help = descs ? descs + blockIdx.x : nullptr;
     while (true) {
@@ -473,7 +562,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         __syncthreads();
         if (b >= B) {
             // no solve left for this CTA: lend its threads to the relax passes of the solves still running
-            if (descs) help_loop<R, GEO>(m.geo, works, descs, gridDim.x, counters, counters + 1, B);
+            if (descs) help_loop<R, GEO, CAUSAL>(m.geo, works, descs, n_slots, counters, counters + 1, B);
             break;
         }
         const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
@@ -484,10 +573,10 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
         bfs_run_cta<R>(m, w, src, S);
         const ull t1 = global_timer();
         const u32 nl = (u32)w.ctrl[C_NLIMITS], p = (u32)w.ctrl[C_REACHED];
-        layout_rows_thread<R>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
+        layout_rows_thread<R, CAUSAL>(m, w, 0u, p, threadIdx.x, blockDim.x, sent, [](const u32 *q) { return *q; });
         __syncthreads();
         const ull t2 = global_timer();
-        const u32 d = ptp_run<R, TeamCta, false, 1, false, GEO>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr, help, counters);
+        const u32 d = ptp_run<R, TeamCta, false, 1, false, GEO, CAUSAL>(t, m, w, src, S, nl, p, sent, s_wl, m.ring_symmetric != 0, nullptr, help, counters);
         scatter_run<R, TeamCta, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -502,14 +591,71 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
             atomicAdd(totals + 3, (ull)(nl ? nl - 1 : 0));
             atomicAdd(totals + 4, (ull)p);
             atomicAdd(totals + 5, w.ctrl[C_RELAXED]);
+            if (w.ctrl[C_ERROR]) atomicMax(totals + 9, w.ctrl[C_ERROR]); // device watchdog (elastic chunks): the host must know
         }
     }
 }
 
+// Batched solves, a TEAM of CTAs per solve. With one CTA per solve 148 solves are in flight and their windows
+// (rows + two distance buffers of ~10^5 vertices each) add up to ~1.5 GB: every Jacobi iteration re-streams its window
+// from HBM and every dependent gather pays DRAM latency. With teams of `team_size` CTAs only gridDim / team_size solves
+// are in flight, each finishing team_size times sooner, so the windows of all of them together stay resident in the
+// 126 MB L2 for the 30-60 iterations a vertex spends in a window. The price is a grid barrier among the team's CTAs
+// per iteration (1 us against ~20 us of relaxation work per iteration). Every phase is the whole-GPU code of the
+// single solve (bfs_run, layout_run, ptp_run, scatter_run on a TeamGrid); teams take solves from one queue, the index
+// travels in the barrier word so that every CTA of the team sees the same one.
+template <class R, bool GEO, bool CAUSAL>
+__global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
+k_batched_teams(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
+                ull *queue, ull *totals, ull *bars, u32 team_size)
+{
+    const u32 team_id = blockIdx.x / team_size;
+    TeamGrid t{bars + (size_t)team_id * 16, 0, team_id * team_size, team_size};
+    const Work<R> w = works[team_id];
+    t.err = w.ctrl + C_ERROR;
+    const bool lead = blockIdx.x == t.cta0 && threadIdx.x == 0;
+    while (!t.dead) {
+        const ull word = t.sync_full(0u, lead ? atomicAdd(queue, 1ull) : 0ull);
+        const u32 b = (u32)(word >> 24);
+        if (b >= B) break;
+        const ull o0 = offsets ? offsets[first + b] : (ull)(first + b);
+        const u32 S = offsets ? (u32)(offsets[first + b + 1] - o0) : 1u;
+        const u32 *src = sources + o0;
+        if (lead) { w.ctrl[C_OVFALLOC] = 0; w.ctrl[C_RELAXED] = 0; }
+        const ull t0 = global_timer();
+        bfs_run<R, TeamGrid, false>(t, m, w, src, S, NIL, sent);
+        const u32 nl = (u32)TeamGrid::ld_sync(w.ctrl + C_NLIMITS), p = (u32)TeamGrid::ld_sync(w.ctrl + C_REACHED);
+        const ull t1 = global_timer();
+        layout_rows_thread<R, CAUSAL>(m, w, 0u, p, t.cta() * blockDim.x + threadIdx.x, t.nctas() * blockDim.x, sent,
+                                      [](const u32 *q) { return TeamGrid::ld(q); });
+        t.sync();
+        const ull t2 = global_timer();
+        const u32 d = ptp_run<R, TeamGrid, false, 1, false, GEO, CAUSAL>(t, m, w, src, S, nl, p, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
+        scatter_run<R, TeamGrid, false>(t, m, w, d, rows + (size_t)b * m.V, nullptr, 0u);
+        t.sync(); // every CTA's share of C_RELAXED is in; the workspace may be reused
+        if (lead) {
+            const ull t3 = global_timer();
+            atomicAdd(totals + 6, t1 - t0); // per-phase device time summed over solves (ns)
+            atomicAdd(totals + 7, t2 - t1);
+            atomicAdd(totals + 8, t3 - t2);
+            atomicAdd(totals + 0, w.ctrl[C_ITER]);
+            atomicAdd(totals + 1, w.ctrl[C_UPDATES]);
+            atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
+            atomicAdd(totals + 3, (ull)(nl ? nl - 1 : 0));
+            atomicAdd(totals + 4, (ull)p);
+            atomicAdd(totals + 5, *(volatile ull *)(w.ctrl + C_RELAXED));
+        }
+    }
+    if (lead && *(volatile ull *)(w.ctrl + C_ERROR)) atomicMax(totals + 9, *(volatile ull *)(w.ctrl + C_ERROR));
+}
+
 // arg-max of |x| with the smallest index on ties (cublasI?amax semantics, src/cuda/geodesics_ptp.cu:139-141);
 // appends the winner to the sample list. Single CTA: the array is read once, bandwidth-trivial next to a solve.
-template <class R> __global__ void __launch_bounds__(1024) k_argmax_append(const R *__restrict__ x, u32 V, u32 *samples, u32 n, R *maxval)
+template <class R> __global__ void __launch_bounds__(1024)
+k_argmax_append(const R *__restrict__ x, u32 V, u32 *samples, u32 n, R *maxval, const ull *ctrl, ull *sticky)
 {
+    // the solve that produced x ran just before in this stream: carry its watchdog word over (ctrl is cleared per solve)
+    if (threadIdx.x == 0 && ctrl[C_ERROR]) *sticky = ctrl[C_ERROR];
     __shared__ R s_v[32];
     __shared__ u32 s_i[32];
     R bv = R(-1);
@@ -549,6 +695,7 @@ struct DevBuf {
 } // namespace
 
 struct ptp_mesh {
+    std::mutex mu; // one workspace per mesh: calls on the same handle are serialised (different handles run concurrently)
     int device = 0;
     int real_size = 0;
     u64 V = 0, H = 0;
@@ -558,6 +705,7 @@ struct ptp_mesh {
     u32 *ring8 = nullptr;
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
+    unsigned char *safe8 = nullptr; // causal-safe triangle flags, built at the first batched call (k_safe_build)
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
     bool geo_failed = false; // the table did not fit: do not try again
     bool two_failed = false; // the two-launch single solve did not get both kernels resident once: use one launch from now on
@@ -578,10 +726,13 @@ struct ptp_mesh {
     void *h_ctrl = nullptr; // pinned
 
     // batched workspace (lazy)
-    u32 bt_slots = 0;
+    u32 bt_slots = 0;  // per-solve workspaces allocated
+    u32 bt_team = 0;   // CTAs per solve they were laid out for (1 = one CTA per solve)
+    u32 bt_grid = 0;   // CTAs of a batched launch
     u64 bt_scap = 0;
     std::vector<void *> bt_allocs;
-    void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr, *bt_help = nullptr;
+    void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr, *bt_help = nullptr,
+         *bt_bars = nullptr, *bt_ctrl = nullptr;
     u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
 };
 
@@ -609,10 +760,12 @@ template <class R> MeshView<R> mesh_view(const ptp_mesh *m)
     MeshView<R> v;
     v.V = (u32)m->V;
     v.ring_symmetric = m->ring_symmetric ? 1u : 0u;
+    v.newest = opt("newest") ? 1u : 0u;
     v.GT4 = (const typename Ops<R>::vec4 *)m->GT4;
     v.ring8 = m->ring8;
     v.ovf = m->ovf;
     v.geo = (const typename Ops<R>::vec4 *)m->geo;
+    v.safe8 = m->safe8;
     return v;
 }
 
@@ -737,11 +890,7 @@ template <class R> int launch_layout(ptp_mesh *m)
     return PTP_OK;
 }
 
-bool use_staging()
-{
-    static int v = [] { const char *e = getenv("PTP_STAGE"); return e ? atoi(e) : 1; }();
-    return v != 0 && PTP_GRID_MAP == 4;
-}
+bool use_staging() { return opt("stage") != 0 && PTP_GRID_MAP == 4; }
 
 template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
@@ -769,16 +918,12 @@ template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 // number of CTAs given to the BFS/layout team of the fused single-solve kernel (PTP_BFS_CTAS overrides)
 int bfs_ctas(const ptp_mesh *m)
 {
-    static int env = [] { const char *e = getenv("PTP_BFS_CTAS"); return e ? atoi(e) : 0; }();
+    const int env = (int)opt("bfs_ctas");
     int nb = env > 0 ? env : m->num_sms; // default: one BFS CTA and one sweep CTA per SM
     return std::max(1, std::min(nb, 2 * m->num_sms - 1));
 }
 
-bool use_fused()
-{
-    static int v = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 1; }();
-    return v != 0;
-}
+bool use_fused() { return opt("fused") != 0; }
 
 template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 {
@@ -789,7 +934,7 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     // Staging the window in shared memory pays in the stand-alone sweep (1 CTA per SM); with two CTAs per SM it
     // takes 160 KB of the SM's 228 KB L1/shared array away from both teams and measured slower (C3: 32.8 vs
     // 29.6 ms), so the fused kernel runs unstaged unless PTP_STAGE=2.
-    static const bool stage_fused = [] { const char *e = getenv("PTP_STAGE"); return e && atoi(e) == 2; }();
+    const bool stage_fused = opt("stage") == 2;
     u32 staged = (stage_fused && PTP_GRID_MAP == 4) ? 1u : 0u;
     size_t smem = staged ? FUSED_BLOCK * Stage4<R>::bytes_per_thread() : 0;
     int per_sm = 0;
@@ -819,8 +964,7 @@ template <class R> int launch_fused(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
 // Returns PTP_OK and sets *launched = false when the configuration is not available (caller falls back).
 int cluster_size()
 {
-    static int v = [] { const char *e = getenv("PTP_CLUSTER"); return e ? atoi(e) : 8; }();
-    return std::max(1, std::min(v, 16));
+    return std::max(1, std::min((int)opt("cluster"), 16));
 }
 
 // Geometry table (MeshView::geo), built once per mesh on first use. Not fatal when it does not fit: the kernels then
@@ -844,13 +988,23 @@ template <class R> int ensure_geo(ptp_mesh *m, cudaStream_t stream, bool *ok)
     return PTP_OK;
 }
 
+template <class R> int ensure_safe(ptp_mesh *m, cudaStream_t stream)
+{
+    if (m->safe8) return PTP_OK;
+    int rc;
+    if ((rc = dev_alloc(m, (void **)&m->safe8, m->V, nullptr))) return rc;
+    k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8);
+    CK(cudaGetLastError());
+    return PTP_OK;
+}
+
 template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, bool *launched)
 {
     *launched = false;
     // Single solve with the geometry table (PTP_GEO_SINGLE=1, off): takes 3 divisions + 2 square roots per triangle off
     // the dependent FP chain of an iteration (thread-0 stamps on C3: compute 3.2 -> 2.1 us per iteration) but the two
     // extra 32-byte records per lane lengthen the gather phase by as much (1.05 -> 2.0 us): 30.1 vs 28.5 ms per solve.
-    static const bool want_geo = [] { const char *e = getenv("PTP_GEO_SINGLE"); return e ? atoi(e) != 0 : false; }();
+    const bool want_geo = opt("geo_single") != 0;
     bool geo = false;
     int rc;
     if (want_geo && (rc = ensure_geo<R>(m, m->stream, &geo))) return rc;
@@ -862,7 +1016,7 @@ template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, 
                    : (cl ? (void *)k_geodesics_cluster<R, true, false> : (void *)k_geodesics_cluster<R, false, false>);
     // the staged window needs (window + entering topleset) <= groups of the sweep team; with ~110 sweep CTAs the widest
     // C3 windows do not fit and the streamed sweep measured faster unstaged (27.9 vs 29.0 ms): PTP_STAGE=1 turns it on
-    static const bool want_stage = [] { const char *e = getenv("PTP_STAGE"); return e && atoi(e) == 1; }();
+    const bool want_stage = opt("stage") == 1;
     u32 staged = (want_stage && PTP_GRID_MAP == 4) ? 1u : 0u;
     size_t smem = staged ? CLUSTER_BLOCK * Stage4<R>::bytes_per_thread() : 0;
     const int csize = cluster_size();
@@ -905,10 +1059,10 @@ template <class R> int launch_cluster(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, 
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] cluster launch refused (%s): falling back to the two-team kernel\n", cudaGetErrorString(e));
+        if (opt("debug")) fprintf(stderr, "[ptp] cluster launch refused (%s): falling back to the two-team kernel\n", cudaGetErrorString(e));
         return PTP_OK;
     }
-    if (getenv("PTP_DEBUG")) fprintf(stderr, "[ptp] cluster kernel: grid %d, cluster %d, staged %u, smem %zu\n", grid, csize, staged, smem);
+    if (opt("debug")) fprintf(stderr, "[ptp] cluster kernel: grid %d, cluster %d, staged %u, smem %zu\n", grid, csize, staged, smem);
     *launched = true;
     m->last_kernel = sizeof(R) == 8 ? "k_geodesics_cluster<double>" : "k_geodesics_cluster<float>";
     return PTP_OK;
@@ -1208,6 +1362,11 @@ int solve_impl(ptp_mesh *m, const u32 *sources, u32 S, const u32 *limits, u32 nl
     k_inv_init<R><<<(unsigned)((m->V + 255) / 256), 256, 0, m->stream>>>(mv, w);
     k_inv_fill<R><<<(unsigned)((p + 255) / 256), 256, 0, m->stream>>>(mv, w, (u32)p);
     CK(cudaGetLastError());
+    // the caller's `sorted` is only trusted after this check: an entry >= V (NIL padding, which the reference's kernels
+    // tolerate through `if(v < n_vertices)`) would index the mesh tables out of bounds in the layout pass
+    CK(cudaMemcpyAsync((ull *)m->h_ctrl + C_ABORT, (ull *)m->w_ctrl + C_ABORT, 8, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (((const ull *)m->h_ctrl)[C_ABORT]) return fail(PTP_ERR_INVALID, "sorted[0 .. limits.back()) holds a vertex index >= n_vertices");
     if ((rc = launch_layout<R>(m))) return rc;
     CK(cudaEventRecord(m->ev[1], m->stream));
     if ((rc = launch_solve<R>(m, S, clusters != nullptr, cl_fill))) return rc;
@@ -1226,7 +1385,7 @@ template <class R> int pipeline(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
     CK(cudaEventRecord(m->ev[0], m->stream));
     // PTP_FUSED: 5 (default) BFS cluster kernel + sweep kernel side by side, 4 the same two teams in ONE cluster launch,
     // 1 two-team kernel (grid barriers only), 0 three launches, 2 debug (the two teams one after the other)
-    static int dbg = [] { const char *e = getenv("PTP_FUSED"); return e ? atoi(e) : 5; }();
+    const int dbg = (int)opt("fused");
     if (dbg == 2 && !cl) {
         MeshView<R> mv = mesh_view<R>(m);
         Work<R> w = work_view<R>(m);
@@ -1291,14 +1450,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         if (rc) return rc;
         break;
     }
-    if (getenv("PTP_FUSED") && atoi(getenv("PTP_FUSED")) == 2)
+    if (opt("fused") == 2)
         fill_stats(m, st, 2, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
     else if (use_fused()) {
         // one launch: the producer / consumer split comes from %globaltimer stamps written by the kernel
         const ull *c = (const ull *)m->h_ctrl;
         const double t_bfs = c[C_TBFS] > c[C_TSTART] ? (c[C_TBFS] - c[C_TSTART]) * 1e-6 : 0.0;
         const double t_all = ev_ms(m->ev[0], m->ev[2]);
-        if (getenv("PTP_DEBUG")) {
+        if (opt("debug")) {
             fprintf(stderr, "[ptp] producer polls by the sweep team: %llu\n", c[C_ARGMAX]);
             if (c[C_TPHASE + 6]) fprintf(stderr, "[ptp] sweep thread-0 ms: relax %.2f | wait for producers %.2f | barrier %.2f | post-barrier %.2f\n",
                     c[C_TPHASE + 6] * 1e-6, c[C_TPHASE + 7] * 1e-6, c[C_TPHASE + 8] * 1e-6, c[C_TPHASE + 9] * 1e-6);
@@ -1324,28 +1483,51 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
     return PTP_OK;
 }
 
-template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off, u64 rows_elems)
+// CTAs per solve of the batched path: the "team" option, or (0) the default for this mesh
+int batch_team(const ptp_mesh *m)
+{
+    long t = opt("team");
+    if (t <= 0) t = 1;
+    return (int)std::max<long>(1, std::min<long>(t, m->num_sms));
+}
+
+template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off, u64 rows_elems, u32 B)
 {
     int rc;
-    if (m->bt_slots == 0 || m->bt_scap < max_s) {
+    const u32 team = (u32)batch_team(m);
+    int per_sm = 0;
+    if (team > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched_teams<R, false, true>, BatchCfg<R>::BLOCK, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R, false, true>, BatchCfg<R>::BLOCK, 0));
+    if (per_sm < 1) return fail(PTP_ERR_CUDA, "batched kernel does not fit on an SM");
+    // one CTA per solve: every resident CTA may own a solve; teams: one CTA per SM, num_sms / team solves in flight
+    const u32 max_slots = team > 1 ? (u32)m->num_sms / team : (u32)(m->num_sms * per_sm);
+    const u32 want = std::max<u32>(1u, std::min<u32>(max_slots, B));
+    if (m->bt_slots < want || m->bt_scap < max_s || m->bt_team != team) {
         free_list(m, m->bt_allocs);
         m->bt_slots = 0;
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R, true>, BatchCfg<R>::BLOCK, 0));
-        if (per_sm < 1) return fail(PTP_ERR_CUDA, "batched kernel does not fit on an SM");
-        const u32 slots = (u32)(m->num_sms * per_sm);
-        const u64 V = m->V, scap = std::max<u64>(max_s, 16), N = V + scap;
+        m->bt_src = m->bt_off = m->bt_rows = nullptr;
+        m->bt_src_cap = m->bt_off_cap = m->bt_rows_cap = 0;
+        const u64 V = m->V, scap = std::max<u64>(std::max<u64>(max_s, m->bt_scap), 16), N = V + scap;
+        const u64 ovfn = std::max<u64>(m->ovf_total, 4), qb = (N + 1 + 15) / 16 * 16, tileb = 4 * 4096;
+        const u64 per_slot = 8 * V + 4 * N + 4 * V + 4 * (V + 2) + tileb + 4 * sizeof(R) * (N + 1) + 4 * GL * N + 4 * ovfn +
+                             2 * sizeof(R) * (N + 1) + 8 * C_COUNT + 4 * N + 2 * qb + 4096;
+        // as many workspaces as the batch can use and the device can hold (the rows staging buffer comes on top)
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const u64 usable = free_b > sizeof(R) * rows_elems + (256ull << 20) ? free_b - sizeof(R) * rows_elems - (256ull << 20) : 0;
+        const u32 fit = (u32)std::min<u64>(usable / per_slot, 1u << 20);
+        if (fit < 1) return fail(PTP_ERR_CUDA, "not enough device memory for one batched-solve workspace");
+        const u32 slots = std::min(want, fit);
         std::vector<Work<R>> hw(slots);
         auto &tr = m->bt_allocs;
         char *b_key, *b_sorted, *b_inv, *b_limits, *b_tile, *b_pos, *b_ring, *b_ovf, *b_d0, *b_d1, *b_ctrl, *b_wl, *b_q0, *b_q1;
-        const u64 ovfn = std::max<u64>(m->ovf_total, 4);
 #define BT(ptr, per)                                                                     \
     if ((rc = dev_alloc(m, (void **)&(ptr), (u64)(per) * slots, &tr)) != PTP_OK) return rc;
         BT(b_key, 8 * V)
         BT(b_sorted, 4 * N)
         BT(b_inv, 4 * V)
         BT(b_limits, 4 * (V + 2))
-        BT(b_tile, 64)
+        BT(b_tile, tileb)
         BT(b_pos, 4 * sizeof(R) * (N + 1))
         BT(b_ring, 4 * GL * N)
         BT(b_ovf, 4 * ovfn)
@@ -1353,8 +1535,8 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
         BT(b_d1, sizeof(R) * (N + 1))
         BT(b_ctrl, 8 * C_COUNT)
         BT(b_wl, 4 * N)
-        BT(b_q0, (N + 1 + 15) / 16 * 16)
-        BT(b_q1, (N + 1 + 15) / 16 * 16)
+        BT(b_q0, qb)
+        BT(b_q1, qb)
 #undef BT
         for (u32 s = 0; s < slots; s++) {
             Work<R> &w = hw[s];
@@ -1362,7 +1544,7 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
             w.sorted = (u32 *)(b_sorted + (u64)s * 4 * N);
             w.inv = (u32 *)(b_inv + (u64)s * 4 * V);
             w.limits = (u32 *)(b_limits + (u64)s * 4 * (V + 2));
-            w.tile_sum = (u32 *)(b_tile + (u64)s * 64);
+            w.tile_sum = (u32 *)(b_tile + (u64)s * tileb);
             w.posS = (typename Ops<R>::vec4 *)(b_pos + (u64)s * 4 * sizeof(R) * (N + 1));
             w.ringS = (u32 *)(b_ring + (u64)s * 4 * GL * N);
             w.ovfS = (u32 *)(b_ovf + (u64)s * 4 * ovfn);
@@ -1372,17 +1554,19 @@ template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off
             w.toplesets = nullptr;
             w.ctrl = (ull *)(b_ctrl + (u64)s * 8 * C_COUNT);
             w.wl = (u32 *)(b_wl + (u64)s * 4 * N);
-            w.dirty[0] = (unsigned char *)(b_q0 + (u64)s * ((N + 1 + 15) / 16 * 16));
-            w.dirty[1] = (unsigned char *)(b_q1 + (u64)s * ((N + 1 + 15) / 16 * 16));
+            w.dirty[0] = (unsigned char *)(b_q0 + (u64)s * qb);
+            w.dirty[1] = (unsigned char *)(b_q1 + (u64)s * qb);
         }
         if ((rc = dev_alloc(m, &m->bt_works, sizeof(Work<R>) * slots, &tr))) return rc;
         if ((rc = dev_alloc(m, &m->bt_queue, 128, &tr))) return rc;
         if ((rc = dev_alloc(m, &m->bt_help, sizeof(HelpDesc) * slots + 64, &tr))) return rc;
+        if ((rc = dev_alloc(m, &m->bt_bars, 128 * (u64)slots + 128, &tr))) return rc;
         CK(cudaMemcpy(m->bt_works, hw.data(), sizeof(Work<R>) * slots, cudaMemcpyHostToDevice));
+        m->bt_ctrl = b_ctrl;
         m->bt_slots = slots;
+        m->bt_team = team;
+        m->bt_grid = team > 1 ? slots * team : (u32)(m->num_sms * per_sm);
         m->bt_scap = scap;
-        m->bt_src = m->bt_off = m->bt_rows = nullptr;
-        m->bt_src_cap = m->bt_off_cap = m->bt_rows_cap = 0;
     }
     if (m->bt_src_cap < n_src) {
         if ((rc = dev_alloc(m, &m->bt_src, 4 * n_src, &m->bt_allocs))) return rc;
@@ -1424,38 +1608,62 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         const u64 budget = 8ull << 30;
         chunk = std::max<u64>(1, std::min<u64>(B, budget / (sizeof(R) * m->V)));
     }
-    if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V))) return rc;
-    // Geometry table (PTP_GEO=1): the mesh-constant half of update_step (3 of 4 divisions, 2 of 3 square roots) read from
+    if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V, B))) return rc;
+    // Geometry table ("geo" option): the mesh-constant half of update_step (3 of 4 divisions, 2 of 3 square roots) read from
     // a table shared by every solve instead of recomputed. Bit-exact, 25 % fewer instructions per relaxation, and yet
     // measured SLOWER in float (C5: 229-234 vs 239-241 sources/s: +128 B of DRAM traffic per relaxation on a kernel that
     // is bound by memory latency, not issue slots) and only +4 % in double, so it stays opt-in.
-    static const bool use_geo = [] { const char *e = getenv("PTP_GEO"); return e ? atoi(e) != 0 : false; }();
+    const bool use_geo = opt("geo") != 0;
     bool geo_ok = false;
     if (use_geo && (rc = ensure_geo<R>(m, stream, &geo_ok))) return rc;
     CK(cudaMemcpyAsync(m->bt_src, sources, 4 * n_src, cudaMemcpyHostToDevice, stream));
     if (offsets) CK(cudaMemcpyAsync(m->bt_off, offsets, 8 * (u64)(B + 1), cudaMemcpyHostToDevice, stream));
     ull *queue = (ull *)m->bt_queue;
     CK(cudaMemsetAsync(queue, 0, 128, stream));
+    CK(cudaMemsetAsync(m->bt_ctrl, 0, 8 * C_COUNT * (u64)m->bt_slots, stream));
     CK(cudaEventRecord(m->ev[0], stream));
+    // causal skip ("causal" option): needs the per-mesh safe flags and 30-bit ranks; not combined with the geometry table
+    // (whose records are indexed by the un-rotated ring slots)
+    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (1ull << 30);
+    if (causal && (rc = ensure_safe<R>(m, stream))) return rc;
     MeshView<R> mv = mesh_view<R>(m);
     if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
     u64 launches = 0;
+    const u32 team = m->bt_team;
     for (u64 first = 0; first < B; first += chunk) {
         const u32 nb = (u32)std::min<u64>(chunk, B - first);
         R *dst = on_device ? rows + first * m->V : (R *)m->bt_rows;
         CK(cudaMemsetAsync(queue, 0, 8, stream));
-        // elastic mode (PTP_ELASTIC=0 disables): every slot's CTA is launched; those beyond the batch help from the start
-        static const bool elastic = [] { const char *e = getenv("PTP_ELASTIC"); return e ? atoi(e) != 0 : true; }();
-        HelpDesc *descs = elastic ? (HelpDesc *)m->bt_help : nullptr;
-        u32 *counters = (u32 *)((char *)m->bt_help + sizeof(HelpDesc) * m->bt_slots);
-        if (elastic) CK(cudaMemsetAsync(m->bt_help, 0, sizeof(HelpDesc) * m->bt_slots + 64, stream));
-        const u32 grid = elastic ? m->bt_slots : std::min<u32>(m->bt_slots, nb);
-        auto kern = mv.geo ? k_batched<R, true> : k_batched<R, false>;
-        kern<<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, (const Work<R> *)m->bt_works, (const u32 *)m->bt_src,
-                                                   offsets ? (const ull *)m->bt_off : nullptr, (u32)first, nb, dst,
-                                                   (u32)(m->V + m->bt_scap), queue, queue + 1, descs, counters);
-        CK(cudaGetLastError());
-        m->last_kernel = sizeof(R) == 8 ? "k_batched<double>" : "k_batched<float>";
+        const Work<R> *works = (const Work<R> *)m->bt_works;
+        const u32 *d_src = (const u32 *)m->bt_src;
+        const ull *d_off = offsets ? (const ull *)m->bt_off : nullptr;
+        u32 first32 = (u32)first, nb32 = nb, sent = (u32)(m->V + m->bt_scap);
+        ull *totals = queue + 1;
+        if (team > 1) {
+            // a team of CTAs per solve; the teams synchronise with software grid barriers, so every CTA must be resident:
+            // cooperative launch (one CTA per SM)
+            ull *bars = (ull *)m->bt_bars;
+            u32 tsz = team;
+            const u32 teams = std::min<u32>(m->bt_slots, nb);
+            CK(cudaMemsetAsync(bars, 0, 128 * (u64)m->bt_slots + 128, stream));
+            void *fn = mv.geo ? (void *)k_batched_teams<R, true, false>
+                              : (causal ? (void *)k_batched_teams<R, false, true> : (void *)k_batched_teams<R, false, false>);
+            void *args[] = {&mv, &works, &d_src, &d_off, &first32, &nb32, &dst, &sent, &queue, &totals, &bars, &tsz};
+            CK(cudaLaunchCooperativeKernel(fn, dim3(teams * team), dim3(BatchCfg<R>::BLOCK), args, 0, stream));
+            m->last_kernel = sizeof(R) == 8 ? "k_batched_teams<double>" : "k_batched_teams<float>";
+        } else {
+            // elastic mode ("elastic" option): every resident CTA is launched; those without a solve help from the start
+            const bool elastic = opt("elastic") != 0;
+            HelpDesc *descs = elastic ? (HelpDesc *)m->bt_help : nullptr;
+            u32 *counters = (u32 *)((char *)m->bt_help + sizeof(HelpDesc) * m->bt_slots);
+            if (elastic) CK(cudaMemsetAsync(m->bt_help, 0, sizeof(HelpDesc) * m->bt_slots + 64, stream));
+            const u32 grid = elastic ? m->bt_grid : std::min<u32>(m->bt_slots, nb);
+            auto kern = mv.geo ? k_batched<R, true, false> : (causal ? k_batched<R, false, true> : k_batched<R, false, false>);
+            kern<<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, works, d_src, d_off, first32, nb32, dst, sent, queue, totals, descs, counters,
+                                                         m->bt_slots);
+            CK(cudaGetLastError());
+            m->last_kernel = sizeof(R) == 8 ? "k_batched<double>" : "k_batched<float>";
+        }
         launches++;
         if (!on_device)
             CK(cudaMemcpyAsync(rows + first * m->V, m->bt_rows, sizeof(R) * (u64)nb * m->V, cudaMemcpyDeviceToHost, stream));
@@ -1464,6 +1672,12 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     ull tot[16];
     CK(cudaMemcpyAsync(tot, queue, 128, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    if (tot[10]) {
+        static const char *what[] = {"", "grid barrier", "sweep team waiting for toplesets / rows", "layout warp waiting for the BFS",
+                                     "layout warp waiting for its turn to publish", "BFS cluster waiting for its tables", "elastic relax chunks"};
+        return fail(PTP_ERR_CUDA, std::string("device watchdog in a batched solve: a wait did not complete (") + (tot[10] < 7 ? what[tot[10]] : "?") +
+                                      "); rows discarded");
+    }
     if (st) {
         st->iterations = tot[1];
         st->vertex_updates = tot[2];
@@ -1473,8 +1687,8 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         st->relaxations = tot[6];
         st->gpu_launches = launches;
         // CTA-time spent in BFS + layout, and in the sweep, averaged over the CTAs that ran (device timers)
-        const double ctas = (double)std::min<u64>(m->bt_slots, B);
-        if (getenv("PTP_DEBUG"))
+        const double ctas = (double)std::min<u64>(m->bt_slots, B); // (teams: per team)
+        if (opt("debug"))
             fprintf(stderr, "[ptp] batched mean per-CTA ms: bfs %.1f layout %.1f sweep+scatter %.1f\n", tot[7] * 1e-6 / ctas,
                     tot[8] * 1e-6 / ctas, tot[9] * 1e-6 / ctas);
         st->ms_toplesets = (double)(tot[7] + tot[8]) * 1e-6 / ctas;
@@ -1494,29 +1708,48 @@ int fps_impl(ptp_mesh *m, u32 *samples, u32 n_initial, u32 n_total, R radio, u32
     // src/cuda/geodesics_ptp.cu:125: n >= n_vertices is clamped to n_vertices / 2
     u64 want = n_total;
     if (want >= m->V) want = m->V >> 1;
+    if ((rc = ensure_workspace<R>(m, std::max<u64>(want, n_initial), false, false))) return rc;
     u32 n = n_initial;
     R maxd = (R)INFINITY;
-    if ((rc = ensure_workspace<R>(m, std::max<u64>(want, n_initial), false, false))) return rc;
-    CK(cudaMemcpyAsync(m->w_src, samples, 4ull * n, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaEventRecord(m->ev[3], m->stream));
-    u64 launches = 0, iters = 0, updates = 0;
-    // the reference loops `n -= samples.size(); while(n-- && max_dist > radio)` (:127-148)
-    while (n < want && maxd > radio) {
-        CK(cudaMemsetAsync(m->w_ctrl, 0, 8 * C_COUNT, m->stream));
-        if ((rc = pipeline<R>(m, n, false, 0))) return rc;
-        k_argmax_append<R><<<1, 1024, 0, m->stream>>>((const R *)m->w_out, (u32)m->V, (u32 *)m->w_src, n, (R *)m->w_maxval);
-        CK(cudaGetLastError());
-        launches += 4;
-        n++;
-        const bool last = n >= want;
-        if (radio > 0 || last) {
-            // the reference reads the maximum back only when it needs it (:143-144)
-            CK(cudaMemcpyAsync(&maxd, m->w_maxval, sizeof(R), cudaMemcpyDeviceToHost, m->stream));
-            CK(cudaStreamSynchronize(m->stream));
+    u64 launches = 0;
+    for (int attempt = 0;; attempt++) {
+        n = n_initial;
+        maxd = (R)INFINITY;
+        CK(cudaMemcpyAsync(m->w_src, samples, 4ull * n, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemsetAsync(m->w_maxval, 0, 16, m->stream)); // [0] last maximum, [1] sticky watchdog word of the whole run
+        CK(cudaEventRecord(m->ev[3], m->stream));
+        // the reference loops `n -= samples.size(); while(n-- && max_dist > radio)` (:127-148)
+        while (n < want && maxd > radio) {
+            CK(cudaMemsetAsync(m->w_ctrl, 0, 8 * C_COUNT, m->stream));
+            if ((rc = pipeline<R>(m, n, false, 0))) return rc;
+            k_argmax_append<R><<<1, 1024, 0, m->stream>>>((const R *)m->w_out, (u32)m->V, (u32 *)m->w_src, n, (R *)m->w_maxval,
+                                                          (const ull *)m->w_ctrl, (ull *)m->w_maxval + 1);
+            CK(cudaGetLastError());
+            launches += m->last_two ? 3 : 2;
+            n++;
+            const bool last = n >= want;
+            if (radio > 0 || last) {
+                // the reference reads the maximum back only when it needs it (:143-144); the watchdog word comes with it
+                ull hv[2] = {0, 0};
+                CK(cudaMemcpyAsync(hv, m->w_maxval, 16, cudaMemcpyDeviceToHost, m->stream));
+                CK(cudaStreamSynchronize(m->stream));
+                memcpy(&maxd, hv, sizeof(R));
+                if (hv[1]) break; // a solve of this run was ended by the watchdog: its arg-max is void
+            }
         }
-        (void)iters; (void)updates;
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        ull hv[2] = {0, 0};
+        CK(cudaMemcpyAsync(hv, m->w_maxval, 16, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        if (hv[1]) {
+            if (m->last_two && attempt == 0) { // the two-kernel solve did not get both kernels resident: one launch from now on
+                m->two_failed = true;
+                continue;
+            }
+            return fail(PTP_ERR_CUDA, "device watchdog: a wait inside a farthest-point-sampling solve did not complete; samples discarded");
+        }
+        break;
     }
-    CK(cudaEventRecord(m->ev[2], m->stream));
     CK(cudaMemcpyAsync(samples, m->w_src, 4ull * n, cudaMemcpyDeviceToHost, m->stream));
     if ((rc = fetch_ctrl(m))) return rc;
     if (n_out) *n_out = n;
@@ -1524,6 +1757,33 @@ int fps_impl(ptp_mesh *m, u32 *samples, u32 n_initial, u32 n_total, R radio, u32
     fill_stats(m, st, launches, 0, 0, ev_ms(m->ev[3], m->ev[2]));
     if (st) st->ms_solve = st->ms_total;
     return PTP_OK;
+}
+
+template <class R> int update_positions(ptp_mesh *m, const R *GT)
+{
+    CK(cudaSetDevice(m->device));
+    if (!GT) return fail(PTP_ERR_INVALID, "GT is null");
+    void *d_gt = nullptr;
+    CK(cudaMalloc(&d_gt, sizeof(R) * 3 * m->V));
+    auto run = [&]() -> int {
+        CK(cudaMemcpyAsync(d_gt, GT, sizeof(R) * 3 * m->V, cudaMemcpyHostToDevice, m->stream));
+        k_pad_gt<R><<<(unsigned)((m->V * 4 + 255) / 256), 256, 0, m->stream>>>((const R *)d_gt, (R *)m->GT4, (u32)m->V);
+        CK(cudaGetLastError());
+        if (m->safe8) {
+            k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, m->stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8);
+            CK(cudaGetLastError());
+        }
+        if (m->geo) { // the geometry table depends on the positions
+            k_geo_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, m->stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V,
+                                                                              (typename Ops<R>::vec4 *)m->geo);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(m->stream));
+        return PTP_OK;
+    };
+    const int rc = run();
+    cudaFree(d_gt);
+    return rc;
 }
 
 } // namespace
@@ -1663,6 +1923,7 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     cudaFree(m->ring8);
     cudaFree(m->ovf);
     cudaFree(m->geo);
+    cudaFree(m->safe8);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     for (auto &e : m->ev)
         if (e) cudaEventDestroy(e);
@@ -1679,12 +1940,41 @@ uint64_t ptp_mesh_device_bytes(const ptp_mesh_t *m) { return m ? m->bytes : 0; }
 
 #define NEED(m, rs)                                                                     \
     if (!(m)) return fail(PTP_ERR_INVALID, "mesh is null");                             \
-    if ((m)->real_size != (rs)) return fail(PTP_ERR_INVALID, "mesh precision does not match this entry point");
+    if ((m)->real_size != (rs)) return fail(PTP_ERR_INVALID, "mesh precision does not match this entry point"); \
+    std::lock_guard<std::mutex> lock_((m)->mu);
+
+int ptp_set_option(const char *name, long value)
+{
+    if (!name) return fail(PTP_ERR_INVALID, "option name is null");
+    options_init();
+    std::lock_guard<std::mutex> lock(g_opt_mu);
+    for (Option &o : g_options)
+        if (!strcmp(o.name, name)) { o.value = value; return PTP_OK; }
+    return fail(PTP_ERR_INVALID, std::string("unknown option: ") + name);
+}
+
+long ptp_get_option(const char *name)
+{
+    return name ? opt(name) : 0;
+}
+
+const char *ptp_option_name(int index) { return index >= 0 && index < N_OPTIONS ? g_options[index].name : nullptr; }
+const char *ptp_option_doc(int index) { return index >= 0 && index < N_OPTIONS ? g_options[index].doc : nullptr; }
+
+int ptp_mesh_update_positions_f32(ptp_mesh_t *m, const float *GT)
+{
+    NEED(m, 4) return update_positions<float>(m, GT);
+}
+int ptp_mesh_update_positions_f64(ptp_mesh_t *m, const double *GT)
+{
+    NEED(m, 8) return update_positions<double>(m, GT);
+}
 
 int ptp_toplesets(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, uint32_t k, uint32_t *toplesets, uint32_t *sorted,
                   uint64_t scap, uint32_t *limits, uint64_t lcap, uint32_t *n_limits, ptp_stats_t *st)
 {
     if (!m) return fail(PTP_ERR_INVALID, "mesh is null");
+    std::lock_guard<std::mutex> lock_(m->mu);
     return m->real_size == 4 ? toplesets_impl<float>(m, sources, S, k, toplesets, sorted, scap, limits, lcap, n_limits, st)
                              : toplesets_impl<double>(m, sources, S, k, toplesets, sorted, scap, limits, lcap, n_limits, st);
 }

@@ -63,6 +63,15 @@ const char *ptp_last_error(void);           /* thread-local text of the last fai
 int ptp_device_count(void);                 /* number of CUDA devices, <= 0 when none                */
 const char *ptp_version(void);
 
+/* Behaviour switches. Every switch has a name, a default and an environment variable PTP_<NAME IN CAPITALS> that
+ * replaces the default when set (read once, at the first use of the library); ptp_set_option changes it at run time
+ * (takes effect at the next call). ptp_option_name / ptp_option_doc enumerate them (NULL past the end). The switches
+ * select among kernel variants that all produce the same bits, except "newest" (which Jacobi buffer is returned). */
+int ptp_set_option(const char *name, long value);
+long ptp_get_option(const char *name);
+const char *ptp_option_name(int index);
+const char *ptp_option_doc(int index);
+
 /* pinned host memory helpers (optional; any host pointer is accepted by the entry points below) */
 void *ptp_host_alloc(size_t bytes);
 void ptp_host_free(void *p);
@@ -77,6 +86,14 @@ int ptp_mesh_create_f32(const float *GT, const uint32_t *VT, const uint32_t *OT,
 int ptp_mesh_create_f64(const double *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT,
                         uint64_t n_vertices, uint64_t n_half_edges, int device, ptp_mesh_t **out);
 void ptp_mesh_destroy(ptp_mesh_t *mesh);
+/* Replace the vertex positions of a resident mesh (GT[V][3], same connectivity): what a caller does after editing a
+ * che in place (noise, smoothing, che::reload of the same topology) instead of destroying and re-creating the handle.
+ * The reference uploads the whole CHE on every solve (src/cuda/che.cu:29-48). */
+int ptp_mesh_update_positions_f32(ptp_mesh_t *mesh, const float *GT);
+int ptp_mesh_update_positions_f64(ptp_mesh_t *mesh, const double *GT);
+/* Threading: a ptp_mesh_t owns ONE solver workspace. Calls on the same handle are serialised by the library (a mutex
+ * per handle); calls on different handles — other meshes, or the same mesh uploaded to other devices — run
+ * concurrently. ptp_last_error() is per thread. */
 /* name of the dominant kernel of the last solve on this mesh (measurement: which single-solve variant ran) */
 const char *ptp_mesh_last_kernel(const ptp_mesh_t *mesh);
 

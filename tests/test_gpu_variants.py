@@ -22,6 +22,10 @@ VARIANTS = [
     ("three-launches-unstaged", {"PTP_FUSED": "0", "PTP_STAGE": "0"}, "k_solve_grid"),
     ("geometry-table", {"PTP_GEO": "1", "PTP_GEO_SINGLE": "1"}, None),
     ("no-elastic", {"PTP_ELASTIC": "0"}, None),
+    ("no-causal-skip", {"PTP_CAUSAL": "0"}, None),
+    ("batched-teams-of-4", {"PTP_TEAM": "4"}, None),
+    ("batched-teams-of-37-no-causal", {"PTP_TEAM": "37", "PTP_CAUSAL": "0"}, None),
+    ("newest-buffer-off-explicit", {"PTP_NEWEST": "0"}, None),
 ]
 
 

@@ -1,0 +1,83 @@
+"""GPU: this repo against the reference's OWN CUDA code (src/cuda/geodesics_ptp*.cu, compiled unmodified for sm_100a
+into oracle/_ref/libgproshan_ref_cuda_*.so and run in a subprocess, tests/ref_gpu_run.py).
+
+The reference's kernels are compiled with FMA contraction and return the buffer written last, so distances are compared
+within a tolerance (1e-9 relative in double) and with the `newest` option; what must be EQUAL is what does not depend
+on the last bits: the Voronoi labels (rule of src/cuda/geodesics_ptp.cu:257-282) and the
+farthest-point samples (src/cuda/geodesics_ptp.cu:87-172)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gproshan_b200 import api
+from ref_gpu_run import case_mesh, ref_cuda_path
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_ref(args, out):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "ref_gpu_run.py")] + args + [str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return np.load(out)
+
+
+def need_ref(dtype):
+    if not os.path.exists(ref_cuda_path(dtype)):
+        pytest.skip("reference CUDA build not present (make -C oracle refgpu needs /root/reference)")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_cluster_rule_equals_reference_cuda_kernel(dtype, oracle, tmp_path):
+    """a6: labels from relax_ptp's cluster rule, executed by the reference's own kernel, equal ours vertex for vertex."""
+    need_ref(dtype)
+    ref = run_ref(["clusters", "f32" if dtype == np.float32 else "f64"], tmp_path / "ref.npz")
+    mesh, src = case_mesh("clusters", dtype)
+    try:
+        api.set_option("newest", 1)  # the buffer the reference's CUDA code copies back (src/cuda/geodesics_ptp.cu:60-66)
+        with api.DeviceMesh(mesh, 0) as dm:
+            d_new, cl_new, _ = dm.geodesics(src, clusters=True, cluster_fill=0)
+    finally:
+        api.set_option("newest", 0)
+    with api.DeviceMesh(mesh, 0) as dm:
+        d_old, cl_old, _ = dm.geodesics(src, clusters=True, cluster_fill=0)
+    assert np.array_equal(d_old, ref["cpu"]), "older buffer == the reference's CPU PTP, bit for bit"
+    tol = 1e-9 if dtype == np.float64 else 2e-4   # FMA contraction in the reference's kernels; float drifts further
+    fin = np.isfinite(ref["dist"])
+    assert np.array_equal(fin, np.isfinite(d_new))
+    rel = np.abs(d_new[fin] - ref["dist"][fin]) / np.maximum(ref["dist"][fin], 1e-30)
+    assert rel.max() <= tol, rel.max()
+    assert ref["clusters"].min() >= 1 and ref["clusters"].max() <= len(src)
+    mism = int((cl_new != ref["clusters"]).sum())
+    if dtype == np.float64:
+        assert mism == 0, f"{mism} labels differ from the reference's CUDA kernel"
+    else:
+        assert mism <= 3, f"{mism} labels differ (float: last-bit ties at Voronoi borders may fall either way under FMA)"
+    # the labels of the two buffers can only differ where the last iteration still moved a label
+    assert (cl_new != cl_old).mean() < 0.01
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_fps_equals_reference_cuda(dtype, tmp_path):
+    """f1: farthest_point_sampling_ptp_gpu of the reference vs ptp_farthest_point_sampling_* (with `newest`, which is what
+    the reference's arg-max reads)."""
+    need_ref(dtype)
+    n = 12
+    ref = run_ref(["fps", "f32" if dtype == np.float32 else "f64", str(n), "0"], tmp_path / "fps.npz")
+    mesh, src = case_mesh("fps", dtype)
+    try:
+        api.set_option("newest", 1)
+        with api.DeviceMesh(mesh, 0) as dm:
+            got, md = dm.farthest_point_sampling(src, n)
+    finally:
+        api.set_option("newest", 0)
+    assert got.size == ref["samples"].size == n
+    same = int((got == ref["samples"]).sum())
+    if dtype == np.float64:
+        assert np.array_equal(got, ref["samples"]), (got, ref["samples"])
+        assert abs(md - float(ref["max_dist"])) <= 1e-9 * md
+    else:
+        assert same >= n - 2, (got, ref["samples"])  # float + FMA: an arg-max tie may fall on a neighbouring vertex

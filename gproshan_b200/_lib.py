@@ -38,7 +38,8 @@ SYMBOLS = [
     "ptp_mesh_create_f32", "ptp_mesh_create_f64", "ptp_mesh_destroy", "ptp_mesh_last_kernel", "ptp_che_build", "ptp_mesh_n_vertices",
     "ptp_mesh_n_half_edges", "ptp_mesh_real_size", "ptp_mesh_device", "ptp_mesh_device_bytes",
     "ptp_toplesets", "ptp_solve_f32", "ptp_solve_f64", "ptp_geodesics_f32", "ptp_geodesics_f64",
-    "ptp_solve_batched_f32", "ptp_solve_batched_f64",
+    "ptp_geodesics_error_iter_f32", "ptp_geodesics_error_iter_f64",
+    "ptp_solve_batched_f32", "ptp_solve_batched_f64", "ptp_solve_batched_multi_f32", "ptp_solve_batched_multi_f64",
     "ptp_farthest_point_sampling_f32", "ptp_farthest_point_sampling_f64", "ptp_debug_barrier_ns",
 ]
 
@@ -79,6 +80,10 @@ def lib():
         f.argtypes = [vp, u32p, C.c_uint32, rp, u32p, C.c_uint32, u32p, C.c_uint64, sp]
         f = getattr(L, f"ptp_solve_batched_{suf}")
         f.argtypes = [vp, u32p, u64p, C.c_uint32, C.c_uint64, vp, C.c_int, vp, sp]
+        f = getattr(L, f"ptp_geodesics_error_iter_{suf}")
+        f.argtypes = [vp, u32p, C.c_uint32, rp, rp, u32p, rp, C.c_uint32, u32p, sp]
+        f = getattr(L, f"ptp_solve_batched_multi_{suf}")
+        f.argtypes = [C.POINTER(vp), C.c_int, u32p, u64p, C.c_uint32, C.c_uint64, vp, C.c_int, sp]
         f = getattr(L, f"ptp_farthest_point_sampling_{suf}")
         f.argtypes = [vp, u32p, C.c_uint32, C.c_uint32, ct, u32p, rp, sp]
     L.ptp_che_build.argtypes = [u32p, C.c_uint64, C.c_uint64, u32p, u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]

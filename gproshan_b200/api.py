@@ -171,6 +171,22 @@ class DeviceMesh:
             srt = srt[:st.n_reached]
         return dist, cl, srt
 
+    # ---- per-iteration error (iter_error_run_ptp_gpu, src/cuda/test_geodesics_ptp.cu:164-211)
+    def error_per_iteration(self, sources, exact, capacity: int = 4096):
+        """-> (iterations, errors in %, final distances): one record per iteration whose window ends at the last topleset"""
+        src = _u32(sources)
+        ex = np.ascontiguousarray(exact, dtype=self.dtype)
+        assert ex.size == self.n_vertices
+        dist = np.empty(self.n_vertices, dtype=self.dtype)
+        it = np.empty(capacity, dtype=np.uint32)
+        er = np.empty(capacity, dtype=self.dtype)
+        n = C.c_uint32()
+        st = Stats()
+        check(getattr(_lib.lib(), f"ptp_geodesics_error_iter_{self.suf}")(self._h, _p(src), src.size, _p(ex, self.ct), _p(dist, self.ct),
+                                                                          _p(it), _p(er, self.ct), capacity, C.byref(n), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return it[:n.value].copy(), er[:n.value].copy(), dist
+
     # ---- batched independent solves (distance-matrix rows)
     def solve_batched(self, sources, offsets=None, rows=None, rows_device_ptr: int | None = None, stream: int | None = None):
         """One solve per source (offsets=None) or per source set sources[offsets[b]:offsets[b+1]].
@@ -206,6 +222,28 @@ class DeviceMesh:
                                                                             C.byref(n_out), C.byref(md), C.byref(st)))
         self.last_stats = st.as_dict()
         return buf[:n_out.value].copy(), md.value
+
+
+def solve_batched_multi(meshes, sources, offsets=None, rows=None, rows_device_ptr: int | None = None):
+    """ptp_solve_batched_multi_*: one process, several devices. `meshes` = DeviceMesh objects of the same mesh on different
+    devices; rows land in a host array (allocated if None) or, with rows_device_ptr, assembled on meshes[0]'s device (NCCL)."""
+    m0 = meshes[0]
+    src = _u32(sources)
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+    B = src.size if off is None else off.size - 1
+    hs = (C.c_void_p * len(meshes))(*[m._h for m in meshes])
+    st = Stats()
+    fn = getattr(_lib.lib(), f"ptp_solve_batched_multi_{m0.suf}")
+    if rows_device_ptr is not None:
+        check(fn(hs, len(meshes), _p(src), _p(off, C.c_uint64), B, src.size, C.c_void_p(rows_device_ptr), 1, C.byref(st)))
+        m0.last_stats = st.as_dict()
+        return None
+    if rows is None:
+        rows = np.empty((B, m0.n_vertices), dtype=m0.dtype)
+    assert rows.dtype == m0.dtype and rows.flags.c_contiguous and rows.size == B * m0.n_vertices
+    check(fn(hs, len(meshes), _p(src), _p(off, C.c_uint64), B, src.size, C.c_void_p(rows.ctypes.data), 0, C.byref(st)))
+    m0.last_stats = st.as_dict()
+    return rows
 
 
 @dataclass

@@ -5,11 +5,15 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <dlfcn.h>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +62,8 @@ Option g_options[] = {
     {"team", 0, "batched solves: CTAs per solve (0 = default for the mesh size, 1 = one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
+    {"gather_chunks", 2, "ptp_solve_batched_multi_*: each device's shard is solved in this many pieces; the NCCL transfer of a "
+                         "piece to the root device runs while the next piece is being solved"},
     {"profile_range", 0, "bracket every single solve with cudaProfilerStart/Stop (ncu --replay-mode range / app-range)"},
     {"debug", 0, "print per-phase device timers to stderr"},
 };
@@ -430,6 +436,13 @@ template <class R> __global__ void k_inv_fill(MeshView<R> m, Work<R> w, u32 p)
     }
 }
 
+// exact distances into rank order (measurement mode of the sweep: Work::exactS)
+template <class R> __global__ void k_gather_exact(Work<R> w, const R *__restrict__ exact, R *__restrict__ exactS)
+{
+    const u32 p = (u32)w.ctrl[C_REACHED];
+    for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < p; r += gridDim.x * blockDim.x) exactS[r] = exact[w.sorted[r]];
+}
+
 template <class R> __global__ void __launch_bounds__(FLAT_BLOCK) k_layout(MeshView<R> m, Work<R> w, u32 sent)
 {
     TeamFlat t;
@@ -734,6 +747,12 @@ struct ptp_mesh {
     void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr, *bt_help = nullptr,
          *bt_bars = nullptr, *bt_ctrl = nullptr;
     u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
+
+    // multi-device batched solves: this device's shard of the rows before it travels to the root device, comm stream
+    void *mg_rows = nullptr;
+    u64 mg_rows_cap = 0;
+    cudaStream_t mg_stream = nullptr;
+    cudaEvent_t mg_ev = nullptr;
 };
 
 namespace {
@@ -892,10 +911,13 @@ template <class R> int launch_layout(ptp_mesh *m)
 
 bool use_staging() { return opt("stage") != 0 && PTP_GRID_MAP == 4; }
 
-template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill)
+template <class R> int launch_solve(ptp_mesh *m, u32 S, bool cl, u32 cl_fill, const R *exactS = nullptr, double *iter_err = nullptr, u32 iter_cap = 0)
 {
     MeshView<R> mv = mesh_view<R>(m);
     Work<R> w = work_view<R>(m);
+    w.exactS = exactS;
+    w.iter_err = iter_err;
+    w.iter_cap = iter_cap;
     int grid;
     void *fn = cl ? (void *)k_solve_grid<R, true> : (void *)k_solve_grid<R, false>;
     int rc = cl ? coop_grid(k_solve_grid<R, true>, SOLVE_BLOCK, m, &grid) : coop_grid(k_solve_grid<R, false>, SOLVE_BLOCK, m, &grid);
@@ -1436,11 +1458,6 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         if ((rc = pipeline<R>(m, S, clusters != nullptr, cl_fill))) return rc;
         CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
         if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
-        if (sorted_index) {
-            // p is only known on the device; copy what the caller can hold and validate afterwards
-            const u64 n = std::min<u64>(scap, m->V + S);
-            CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * n, cudaMemcpyDeviceToHost, m->stream));
-        }
         rc = fetch_ctrl(m);
         if (rc && m->last_two && attempt == 0 && ((const ull *)m->h_ctrl)[C_ERROR]) {
             // the two kernels did not become resident together (the watchdog ended them): one launch from now on
@@ -1478,8 +1495,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
         fill_stats(m, st, m->last_two ? 2 : 1, t_bfs, c[C_TEND] > c[C_TSTART] ? (c[C_TEND] - c[C_TSTART]) * 1e-6 : t_all, t_all);
     } else
         fill_stats(m, st, 3, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
-    if (sorted_index && scap < ((const ull *)m->h_ctrl)[C_REACHED])
-        return fail(PTP_ERR_CAPACITY, "sorted_index buffer too small (needs V + duplicate sources)");
+    if (sorted_index) {
+        // exactly the limits.back() entries che::compute_toplesets writes (src/che.cpp:555-592); the rest of the caller's
+        // array is left as it was (geodesics::geodesics presets it to NIL, src/geodesics.cpp:26)
+        const u64 p = ((const ull *)m->h_ctrl)[C_REACHED];
+        CK(cudaMemcpyAsync(sorted_index, m->w_sorted, 4 * std::min<u64>(scap, p), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        if (scap < p) return fail(PTP_ERR_CAPACITY, "sorted_index buffer too small (needs V + duplicate sources)");
+    }
     return PTP_OK;
 }
 
@@ -1489,6 +1512,57 @@ int batch_team(const ptp_mesh *m)
     long t = opt("team");
     if (t <= 0) t = 1;
     return (int)std::max<long>(1, std::min<long>(t, m->num_sms));
+}
+
+// Per-iteration error of a solve (src/cuda/test_geodesics_ptp.cu:164-211, written to `<mesh>_error.iter` by
+// src/test_geodesics_ptp.cpp:198-214): the three-launch path (BFS, layout, stand-alone sweep) with the sweep in
+// measurement mode. errors[k] = 100 / (V - S) * sum over exact > 0 of |dist - exact| / exact after iteration iters[k],
+// for every iteration whose window ends at the last topleset.
+template <class R>
+int error_iter_impl(ptp_mesh *m, const u32 *sources, u32 S, const R *exact, R *dist, u32 *iters, R *errors, u32 cap, u32 *n_out,
+                    ptp_stats_t *st)
+{
+    int rc;
+    CK(cudaSetDevice(m->device));
+    if ((rc = check_sources(m, sources, S))) return rc;
+    if (!exact || !iters || !errors || !n_out || cap == 0) return fail(PTP_ERR_INVALID, "exact, iters, errors (capacity > 0) and n_out are required");
+    if ((rc = ensure_workspace<R>(m, S, false, false))) return rc;
+    R *d_exact = nullptr, *d_exactS = nullptr;
+    double *d_rec = nullptr;
+    std::vector<double> rec(2 * (size_t)cap);
+    auto run = [&]() -> int {
+        CK(cudaMalloc(&d_exact, sizeof(R) * m->V));
+        CK(cudaMalloc(&d_exactS, sizeof(R) * (m->V + m->ws_scap + 1)));
+        CK(cudaMalloc(&d_rec, 16 * (size_t)cap));
+        CK(cudaMemcpyAsync(d_exact, exact, sizeof(R) * m->V, cudaMemcpyHostToDevice, m->stream));
+        CK(cudaMemsetAsync(d_rec, 0, 16 * (size_t)cap, m->stream));
+        int r2;
+        if ((r2 = upload_sources<R>(m, sources, S))) return r2;
+        CK(cudaEventRecord(m->ev[0], m->stream));
+        if ((r2 = launch_bfs<R>(m, S, NIL, false))) return r2;
+        if ((r2 = launch_layout<R>(m))) return r2;
+        k_gather_exact<R><<<m->num_sms * 4, 256, 0, m->stream>>>(work_view<R>(m), d_exact, d_exactS);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(m->ev[1], m->stream));
+        if ((r2 = launch_solve<R>(m, S, false, 0, d_exactS, d_rec, cap))) return r2;
+        CK(cudaEventRecord(m->ev[2], m->stream));
+        if (dist) CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaMemcpyAsync(rec.data(), d_rec, 16 * (size_t)cap, cudaMemcpyDeviceToHost, m->stream));
+        return fetch_ctrl(m);
+    };
+    rc = run();
+    cudaFree(d_exact); cudaFree(d_exactS); cudaFree(d_rec);
+    if (rc) return rc;
+    const ull *c = (const ull *)m->h_ctrl;
+    const u32 n = (u32)std::min<ull>(c[C_NITERR], cap);
+    const bool all_reached = c[C_REACHED] >= m->V; // an unreached vertex with exact > 0 makes the reference's sum infinite
+    for (u32 k = 0; k < n; k++) {
+        iters[k] = (u32)rec[2 * k];
+        errors[k] = all_reached ? (R)(rec[2 * k + 1] * 100.0 / (double)(m->V - S)) : (R)INFINITY;
+    }
+    *n_out = n;
+    fill_stats(m, st, 4, ev_ms(m->ev[0], m->ev[1]), ev_ms(m->ev[1], m->ev[2]), ev_ms(m->ev[0], m->ev[2]));
+    return PTP_OK;
 }
 
 template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off, u64 rows_elems, u32 B)
@@ -1678,6 +1752,16 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         return fail(PTP_ERR_CUDA, std::string("device watchdog in a batched solve: a wait did not complete (") + (tot[10] < 7 ? what[tot[10]] : "?") +
                                       "); rows discarded");
     }
+#ifdef PTP_COUNT_TRI
+    {
+        ull c[4];
+        cudaMemcpyFromSymbol(c, g_tri_cnt, sizeof c);
+        fprintf(stderr, "[ptp] causal: relaxations %llu, triangles %llu, evaluated %llu (%.1f %%), warp-level lane-slots %llu (%.1f %% of triangles)\n",
+                c[3], c[0], c[1], 100.0 * c[1] / (double)c[0], c[2], 100.0 * c[2] / (double)c[0]);
+        ull z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_tri_cnt, z, sizeof z);
+    }
+#endif
     if (st) {
         st->iterations = tot[1];
         st->vertex_updates = tot[2];
@@ -1784,6 +1868,235 @@ template <class R> int update_positions(ptp_mesh *m, const R *GT)
     const int rc = run();
     cudaFree(d_gt);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched solves over several devices of one process (ptp_solve_batched_multi_*). gproshan is a single C++ process
+// (the caller shape is src/sampling.cpp:23-34): one host thread per device drives that device's shard through
+// batched_impl; with host rows every device copies its rows straight into the caller's matrix, with device rows the
+// shards travel to the root device over NVLink with NCCL (grouped ncclSend / ncclRecv), piece by piece, while the next
+// piece is being solved. NCCL is loaded at run time (dlopen: the process may already hold one, e.g. PyTorch's).
+
+struct Nccl {
+    typedef void *comm_t;
+    int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+Nccl &nccl()
+{
+    static Nccl n = [] {
+        Nccl x;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { x.why = std::string("libnccl.so.2 cannot be loaded: ") + dlerror(); return x; }
+        auto sym = [&](const char *name) { return dlsym(h, name); };
+        x.CommInitAll = (decltype(x.CommInitAll))sym("ncclCommInitAll");
+        x.CommDestroy = (decltype(x.CommDestroy))sym("ncclCommDestroy");
+        x.Send = (decltype(x.Send))sym("ncclSend");
+        x.Recv = (decltype(x.Recv))sym("ncclRecv");
+        x.GroupStart = (decltype(x.GroupStart))sym("ncclGroupStart");
+        x.GroupEnd = (decltype(x.GroupEnd))sym("ncclGroupEnd");
+        x.GetErrorString = (decltype(x.GetErrorString))sym("ncclGetErrorString");
+        x.ok = x.CommInitAll && x.CommDestroy && x.Send && x.Recv && x.GroupStart && x.GroupEnd && x.GetErrorString;
+        if (!x.ok) x.why = "libnccl.so.2 lacks ncclCommInitAll / ncclSend / ncclRecv";
+        return x;
+    }();
+    return n;
+}
+
+// communicators are kept per device list (creating them costs ~100 ms)
+struct CommSet { std::vector<int> devs; std::vector<Nccl::comm_t> comms; };
+std::mutex g_comm_mu;
+std::vector<CommSet> g_comm_sets;
+
+int get_comms(const std::vector<int> &devs, std::vector<Nccl::comm_t> *out)
+{
+    Nccl &n = nccl();
+    if (!n.ok) return fail(PTP_ERR_CUDA, n.why);
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    for (CommSet &c : g_comm_sets)
+        if (c.devs == devs) { *out = c.comms; return PTP_OK; }
+    CommSet c;
+    c.devs = devs;
+    c.comms.resize(devs.size());
+    const int rc = n.CommInitAll(c.comms.data(), (int)devs.size(), devs.data());
+    if (rc != 0) return fail(PTP_ERR_CUDA, std::string("ncclCommInitAll: ") + n.GetErrorString(rc));
+    g_comm_sets.push_back(c);
+    *out = c.comms;
+    return PTP_OK;
+}
+
+struct Rendezvous { // reusable barrier for the device threads + the coordinator
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0, generation = 0;
+    explicit Rendezvous(int n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const int g = generation;
+        if (++waiting == n) { waiting = 0; generation++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != g; });
+    }
+};
+
+template <class R>
+int batched_multi_impl(ptp_mesh *const *ms, int G, const u32 *sources, const u64 *offsets, u32 B, u64 n_src, R *rows, int on_device,
+                       ptp_stats_t *st)
+{
+    if (!ms || G < 1) return fail(PTP_ERR_INVALID, "need at least one mesh handle");
+    if (B == 0 || !rows || !sources) return fail(PTP_ERR_INVALID, "empty batch or null pointer");
+    if (!offsets && n_src != B) return fail(PTP_ERR_INVALID, "without offsets n_sources must equal n_batch");
+    std::vector<int> devs(G);
+    for (int g = 0; g < G; g++) {
+        if (!ms[g]) return fail(PTP_ERR_INVALID, "null mesh handle");
+        if (ms[g]->real_size != (int)sizeof(R)) return fail(PTP_ERR_INVALID, "mesh precision does not match this entry point");
+        if (ms[g]->V != ms[0]->V || ms[g]->H != ms[0]->H) return fail(PTP_ERR_INVALID, "the handles must hold the same mesh");
+        devs[g] = ms[g]->device;
+        for (int k = 0; k < g; k++)
+            if (devs[k] == devs[g]) return fail(PTP_ERR_INVALID, "one handle per device: two handles share a device");
+    }
+    const u64 V = ms[0]->V;
+    const bool gather = on_device && G > 1;
+    std::vector<Nccl::comm_t> comms;
+    int rc;
+    if (gather && (rc = get_comms(devs, &comms))) return rc;
+    const int pieces = gather ? (int)std::max<long>(1, std::min<long>(opt("gather_chunks"), 64)) : 1;
+
+    // contiguous block partition of the batch; the first B % G devices get one more
+    std::vector<u64> lo(G + 1, 0);
+    for (int g = 0; g < G; g++) lo[g + 1] = lo[g] + B / G + ((u64)g < B % G ? 1 : 0);
+
+    std::vector<int> codes(G, PTP_OK);
+    std::vector<std::string> errs(G);
+    std::vector<ptp_stats_t> stats(G);
+    Rendezvous meet(G + 1);
+    const auto t_begin = std::chrono::steady_clock::now();
+
+    auto worker = [&](int g) {
+        ptp_mesh *m = ms[g];
+        std::lock_guard<std::mutex> lock(m->mu);
+        memset(&stats[g], 0, sizeof(ptp_stats_t));
+        auto step = [&](int code) { if (code != PTP_OK && codes[g] == PTP_OK) { codes[g] = code; errs[g] = g_err; } return code; };
+        const u64 nb = lo[g + 1] - lo[g];
+        R *dst_base = nullptr;
+        if (cudaSetDevice(m->device) != cudaSuccess) step(fail(PTP_ERR_CUDA, "cudaSetDevice failed"));
+        if (codes[g] == PTP_OK && nb) {
+            if (!on_device) dst_base = rows + lo[g] * V;          // host matrix: this device's rows land in place
+            else if (g == 0) dst_base = rows + lo[g] * V;          // root device: in place in the assembled matrix
+            else {                                                  // peer: staged here, then sent to the root
+                if (m->mg_rows_cap < nb * V) {
+                    cudaFree(m->mg_rows);
+                    m->mg_rows = nullptr;
+                    m->mg_rows_cap = 0;
+                    if (cudaMalloc(&m->mg_rows, sizeof(R) * nb * V) != cudaSuccess) { cudaGetLastError(); step(fail(PTP_ERR_CUDA, "cudaMalloc of the row staging buffer failed")); }
+                    else m->mg_rows_cap = nb * V;
+                }
+                dst_base = (R *)m->mg_rows;
+            }
+        }
+        if (gather && codes[g] == PTP_OK) {
+            if (!m->mg_stream && cudaStreamCreateWithFlags(&m->mg_stream, cudaStreamNonBlocking) != cudaSuccess) step(fail(PTP_ERR_CUDA, "stream creation failed"));
+            if (!m->mg_ev && cudaEventCreateWithFlags(&m->mg_ev, cudaEventDisableTiming) != cudaSuccess) step(fail(PTP_ERR_CUDA, "event creation failed"));
+        }
+        for (int c = 0; c < pieces; c++) {
+            const u64 a = lo[g] + nb * c / pieces, b = lo[g] + nb * (c + 1) / pieces;
+            if (codes[g] == PTP_OK && b > a) {
+                ptp_stats_t s1;
+                memset(&s1, 0, sizeof s1);
+                std::vector<u64> off;
+                const u32 *src = sources + a;
+                u64 ns = b - a;
+                if (offsets) {
+                    off.resize(b - a + 1);
+                    for (u64 k = a; k <= b; k++) off[k - a] = offsets[k] - offsets[a];
+                    src = sources + offsets[a];
+                    ns = offsets[b] - offsets[a];
+                }
+                step(batched_impl<R>(m, src, offsets ? off.data() : nullptr, (u32)(b - a), ns, dst_base + (a - lo[g]) * V, on_device, nullptr, &s1));
+                stats[g].iterations += s1.iterations;
+                stats[g].vertex_updates += s1.vertex_updates;
+                stats[g].relaxations += s1.relaxations;
+                stats[g].n_levels += s1.n_levels;
+                stats[g].n_reached += s1.n_reached;
+                stats[g].gpu_launches += s1.gpu_launches;
+                stats[g].max_window = std::max(stats[g].max_window, s1.max_window);
+                stats[g].ms_toplesets += s1.ms_toplesets;
+                stats[g].ms_solve += s1.ms_solve;
+                stats[g].ms_total += s1.ms_total;
+            }
+            if (gather) {
+                meet.wait(); // piece c is solved on every device (batched_impl returns after its stream has drained)
+                meet.wait(); // the coordinator has enqueued the transfer of piece c; go on with piece c + 1
+            }
+        }
+    };
+
+    std::vector<std::thread> threads;
+    for (int g = 0; g < G; g++) threads.emplace_back(worker, g);
+    int comm_rc = PTP_OK;
+    std::string comm_err;
+    if (gather) {
+        Nccl &n = nccl();
+        const int dt = sizeof(R) == 4 ? 7 : 8; // ncclFloat32 / ncclFloat64
+        for (int c = 0; c < pieces; c++) {
+            meet.wait();
+            bool all_ok = comm_rc == PTP_OK;
+            for (int g = 0; g < G; g++) all_ok = all_ok && codes[g] == PTP_OK;
+            if (all_ok) {
+                int r = n.GroupStart();
+                for (int g = 1; g < G && r == 0; g++) {
+                    const u64 nb = lo[g + 1] - lo[g];
+                    const u64 a = nb * c / pieces, b = nb * (c + 1) / pieces;
+                    if (b == a) continue;
+                    r = n.Send((const R *)ms[g]->mg_rows + a * V, (b - a) * V, dt, 0, comms[g], ms[g]->mg_stream);
+                    if (r == 0) r = n.Recv(rows + (lo[g] + a) * V, (b - a) * V, dt, g, comms[0], ms[0]->mg_stream);
+                }
+                const int r2 = n.GroupEnd();
+                if (r == 0) r = r2;
+                if (r != 0) { comm_rc = PTP_ERR_CUDA; comm_err = std::string("NCCL send/recv: ") + n.GetErrorString(r); }
+            }
+            meet.wait();
+        }
+    }
+    for (std::thread &t : threads) t.join();
+    if (gather && comm_rc == PTP_OK) {
+        for (int g = 0; g < G; g++) {
+            cudaSetDevice(ms[g]->device);
+            if (ms[g]->mg_stream && cudaStreamSynchronize(ms[g]->mg_stream) != cudaSuccess) {
+                comm_rc = PTP_ERR_CUDA;
+                comm_err = "the row transfer to the root device failed";
+            }
+        }
+        cudaSetDevice(ms[0]->device);
+    }
+    for (int g = 0; g < G; g++)
+        if (codes[g] != PTP_OK) return fail(codes[g], "device " + std::to_string(devs[g]) + ": " + errs[g]);
+    if (comm_rc != PTP_OK) return fail(comm_rc, comm_err);
+    if (st) {
+        memset(st, 0, sizeof *st);
+        for (int g = 0; g < G; g++) {
+            st->iterations += stats[g].iterations;
+            st->vertex_updates += stats[g].vertex_updates;
+            st->relaxations += stats[g].relaxations;
+            st->n_levels += stats[g].n_levels;
+            st->n_reached += stats[g].n_reached;
+            st->gpu_launches += stats[g].gpu_launches;
+            st->max_window = std::max(st->max_window, stats[g].max_window);
+            st->ms_toplesets = std::max(st->ms_toplesets, stats[g].ms_toplesets);
+            st->ms_solve = std::max(st->ms_solve, stats[g].ms_total); // slowest device: kernel time of its shard
+        }
+        st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    }
+    return PTP_OK;
 }
 
 } // namespace
@@ -1924,6 +2237,9 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     cudaFree(m->ovf);
     cudaFree(m->geo);
     cudaFree(m->safe8);
+    cudaFree(m->mg_rows);
+    if (m->mg_stream) cudaStreamDestroy(m->mg_stream);
+    if (m->mg_ev) cudaEventDestroy(m->mg_ev);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);
     for (auto &e : m->ev)
         if (e) cudaEventDestroy(e);
@@ -2001,6 +2317,17 @@ int ptp_geodesics_f64(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, double
     NEED(m, 8) return geodesics_impl<double>(m, sources, S, dist, clusters, fill, sorted_index, scap, st);
 }
 
+int ptp_geodesics_error_iter_f32(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, const float *exact, float *dist, uint32_t *iters,
+                                 float *errors, uint32_t cap, uint32_t *n_out, ptp_stats_t *st)
+{
+    NEED(m, 4) return error_iter_impl<float>(m, sources, S, exact, dist, iters, errors, cap, n_out, st);
+}
+int ptp_geodesics_error_iter_f64(ptp_mesh_t *m, const uint32_t *sources, uint32_t S, const double *exact, double *dist, uint32_t *iters,
+                                 double *errors, uint32_t cap, uint32_t *n_out, ptp_stats_t *st)
+{
+    NEED(m, 8) return error_iter_impl<double>(m, sources, S, exact, dist, iters, errors, cap, n_out, st);
+}
+
 int ptp_solve_batched_f32(ptp_mesh_t *m, const uint32_t *sources, const uint64_t *offsets, uint32_t B, uint64_t n_src, float *rows,
                           int on_device, void *stream, ptp_stats_t *st)
 {
@@ -2010,6 +2337,17 @@ int ptp_solve_batched_f64(ptp_mesh_t *m, const uint32_t *sources, const uint64_t
                           int on_device, void *stream, ptp_stats_t *st)
 {
     NEED(m, 8) return batched_impl<double>(m, sources, offsets, B, n_src, rows, on_device, stream, st);
+}
+
+int ptp_solve_batched_multi_f32(ptp_mesh_t *const *meshes, int n_devices, const uint32_t *sources, const uint64_t *offsets, uint32_t B,
+                                uint64_t n_src, float *rows, int on_device, ptp_stats_t *st)
+{
+    return batched_multi_impl<float>(meshes, n_devices, sources, offsets, B, n_src, rows, on_device, st);
+}
+int ptp_solve_batched_multi_f64(ptp_mesh_t *const *meshes, int n_devices, const uint32_t *sources, const uint64_t *offsets, uint32_t B,
+                                uint64_t n_src, double *rows, int on_device, ptp_stats_t *st)
+{
+    return batched_multi_impl<double>(meshes, n_devices, sources, offsets, B, n_src, rows, on_device, st);
 }
 
 int ptp_farthest_point_sampling_f32(ptp_mesh_t *m, uint32_t *samples, uint32_t n_initial, uint32_t n_total, float radio,

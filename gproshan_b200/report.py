@@ -10,8 +10,9 @@ For every mesh it writes what the reference writes (same file names, same line f
   <name>.fps                                  farthest-point-sampling time against the number of samples (:218-229;
                                               cumulative device time at a few sample counts instead of per sample)
 `compute_error` is the reference's (:361-370): 100 / (n - s) * sum over exact > 0 of |dist - exact| / exact.
-The per-iteration error file (`_error.iter`, :198-214) needs a distance snapshot per PTP iteration, which the fused
-kernels do not expose; it is not written.
+  <name>_error.iter / _error_double.iter      per-iteration error (:198-214; iter_error_run_ptp_gpu,
+                                              src/cuda/test_geodesics_ptp.cu:164-211) from ptp_geodesics_error_iter_*: the
+                                              sums are formed on the device, no per-iteration copy of the distances
 
 Exact distances: `<name>.exact` files as the reference reads them (:345-359, one value per vertex), or — for the
 synthetic meshes of this repo — the analytic distance on the smooth surface (great circle on the unit sphere,
@@ -99,6 +100,7 @@ def run(meshes, out_dir: str, n_test: int = 10, device: int = 0, fps_counts=(2, 
                 dist, _, _ = dm.geodesics(source)
                 best = min(best, dm.last_stats["ms_total"] / 1e3)
             stats = dict(dm.last_stats)
+            iter_err = dm.error_per_iteration(source, exact)[:2] if exact is not None else None
             fps = []
             for n in fps_counts:
                 if n < mesh.n_vertices // 2:
@@ -114,6 +116,9 @@ def run(meshes, out_dir: str, n_test: int = 10, device: int = 0, fps_counts=(2, 
             f.writelines(f"{i} {s}\n" for i, s in enumerate(sizes))
         with open(os.path.join(out_dir, name + "_toplesets_sorted.dist"), "w") as f:
             f.writelines(f"{i} {s}\n" for i, s in enumerate(ssorted))
+        if iter_err is not None:
+            with open(os.path.join(out_dir, name + ("_error_double.iter" if double else "_error.iter")), "w") as f:
+                f.writelines(f"{int(i)} {e}\n" for i, e in zip(*iter_err))
         with open(os.path.join(out_dir, name + ".fps"), "w") as f:
             f.writelines(f"{n} {t}\n" for n, t in fps)
         results.append({"name": name, "n_vertices": mesh.n_vertices, "seconds": best, "error_pct": err,

@@ -6,22 +6,38 @@
 // libptp_b200.so (include/ptp_b200.h). See INTEGRATION.md for the CMake change.
 //
 // Differences a caller can observe, all deliberate:
-//   * no cudaDeviceReset() (src/cuda/geodesics_ptp.cu:22,89): the mesh stays resident between calls, keyed by
-//     the che* (call gproshan::ptp_b200_release(mesh) before deleting or editing a mesh);
+//   * no cudaDeviceReset() (src/cuda/geodesics_ptp.cu:22,89): the mesh stays resident between calls (cache below);
 //   * distances are those of parallel_toplesets_propagation_cpu bit for bit (the reference GPU code returns
-//     the other Jacobi buffer and contracts FMAs);
-//   * clusters of unreached vertices are left untouched only in the sense of the reference's host array: they
-//     receive NIL here (the reference uploads and downloads whatever the caller's array held);
+//     the other Jacobi buffer and contracts FMAs); ptp_set_option("newest", 1) — or
+//     PTP_NEWEST=1 in the environment — selects the buffer the reference's CUDA code copies back;
 //   * CUDA failures are reported on stderr and the call returns -1 seconds instead of being ignored.
+//
+// Resident-mesh cache. The reference uploads the whole CHE on every call; here the device copy is kept per che*
+// and VALIDATED on every call against the host tables, so an in-place edit of the che (noise, smoothing, che::reload,
+// a new mesh at a recycled address) is never solved on stale data:
+//   - the four table addresses and the two counts must be unchanged, and
+//   - a fingerprint of GT and of VT must be unchanged: every table entry for meshes up to 2^20 vertices (or always with
+//     PTP_B200_VERIFY=full), a strided sample of 2^16 cache lines per table beyond that (PTP_B200_VERIFY=sample forces
+//     it; a full pass over a 10 M-vertex mesh costs as much as a solve). OT and EVT are functions of VT.
+//   A changed GT fingerprint with unchanged connectivity re-uploads the positions only (ptp_mesh_update_positions_*);
+//   anything else rebuilds the device mesh. ptp_b200_release(che*) drops an entry explicitly.
+// Threading: like the reference (single host thread) the three entry points are not meant to be called
+// concurrently for the SAME che; the cache itself is mutex-protected and the C ABI serialises calls per device mesh.
+// Device: CUDA ordinal from ptp_b200_set_device(int) or PTP_B200_DEVICE (default 0).
 #include "geodesics_ptp.h"
 
 #include "ptp_b200.h"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <map>
+#include <algorithm>
 #include <mutex>
+#include <numeric>
 #include <type_traits>
+#include <utility>
 
 namespace gproshan {
 
@@ -29,46 +45,113 @@ namespace {
 
 constexpr bool kSingle = std::is_same<real_t, float>::value;
 
-struct Resident { ptp_mesh_t *h; size_t nv, nhe; };
-std::map<che *, Resident> g_cache;
+struct Resident {
+    ptp_mesh_t *h;
+    size_t nv, nhe;
+    const void *gt, *vt, *ot, *evt;
+    uint64_t fp_gt, fp_vt;
+    int device;
+};
+std::map<std::pair<che *, int>, Resident> g_cache;
 std::mutex g_mu;
+int g_device = -1;
 
-ptp_mesh_t *resident(che *mesh)
+int device_ordinal()
+{
+    if (g_device < 0) {
+        const char *e = getenv("PTP_B200_DEVICE");
+        g_device = e ? atoi(e) : 0;
+    }
+    return g_device;
+}
+
+// FNV-style fingerprint over 8-byte words: all of them, or (sampled) 2^16 cache lines spread evenly over the table
+uint64_t fingerprint(const void *p, size_t bytes, bool full)
+{
+    const uint64_t *w = (const uint64_t *) p;
+    const size_t n = bytes / 8;
+    uint64_t h = 0xcbf29ce484222325ull ^ bytes;
+    if (full || n <= (size_t(1) << 19)) {
+        uint64_t acc[4] = {h, h ^ 1, h ^ 2, h ^ 3};
+        size_t i = 0;
+        for (; i + 4 <= n; i += 4)
+            for (int k = 0; k < 4; k++) acc[k] = (acc[k] ^ w[i + k]) * 0x100000001b3ull;
+        for (; i < n; i++) acc[0] = (acc[0] ^ w[i]) * 0x100000001b3ull;
+        h = acc[0] ^ (acc[1] * 3) ^ (acc[2] * 5) ^ (acc[3] * 7);
+    } else {
+        const size_t lines = size_t(1) << 16, step = n / lines;
+        for (size_t l = 0; l < lines; l++)
+            for (size_t k = 0; k < 8 && l * step + k < n; k++) h = (h ^ w[l * step + k]) * 0x100000001b3ull;
+    }
+    const unsigned char *tail = (const unsigned char *) p + n * 8;
+    for (size_t i = 0; i < bytes % 8; i++) h = (h ^ tail[i]) * 0x100000001b3ull;
+    return h;
+}
+
+bool verify_full(size_t nv)
+{
+    static const int mode = [] {
+        const char *e = getenv("PTP_B200_VERIFY");
+        return !e ? 0 : (!strcmp(e, "full") ? 1 : (!strcmp(e, "sample") ? 2 : 0));
+    }();
+    return mode == 1 || (mode == 0 && nv <= (size_t(1) << 20));
+}
+
+ptp_mesh_t *resident(che *mesh, int device = -1)
 {
     std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_cache.find(mesh);
+    if (device < 0) device = device_ordinal();
+    CHE tables(mesh); // friend view of GT / VT / OT / EVT (include/che.h:129,134-146; src/che.cpp:36-46)
+    const size_t nv = tables.n_vertices, nhe = tables.n_half_edges;
+    const bool full = verify_full(nv);
+    const uint64_t fp_gt = fingerprint(tables.GT, sizeof(real_t) * 3 * nv, full), fp_vt = fingerprint(tables.VT, sizeof(index_t) * nhe, full);
+    auto it = g_cache.find({mesh, device});
     if (it != g_cache.end()) {
-        if (it->second.nv == mesh->n_vertices() && it->second.nhe == mesh->n_half_edges()) return it->second.h;
-        ptp_mesh_destroy(it->second.h); // same address, different mesh: rebuild
+        Resident &r = it->second;
+        const bool same_topology = r.nv == nv && r.nhe == nhe && r.vt == tables.VT && r.ot == tables.OT && r.evt == tables.EVT &&
+                                   r.fp_vt == fp_vt && r.device == device;
+        if (same_topology && r.gt == tables.GT && r.fp_gt == fp_gt) return r.h;
+        if (same_topology) { // positions edited in place (or re-allocated): refresh them, keep the one-ring tables
+            int rc;
+            if constexpr (kSingle) rc = ptp_mesh_update_positions_f32(r.h, (const float *) tables.GT);
+            else rc = ptp_mesh_update_positions_f64(r.h, (const double *) tables.GT);
+            if (rc == PTP_OK) {
+                r.gt = tables.GT;
+                r.fp_gt = fp_gt;
+                return r.h;
+            }
+            fprintf(stderr, "[ptp_b200] position refresh failed (%s); rebuilding the device mesh\n", ptp_last_error());
+        }
+        ptp_mesh_destroy(r.h); // same address, different mesh: rebuild
         g_cache.erase(it);
     }
-    CHE tables(mesh); // friend view of GT / VT / OT / EVT (include/che.h:129,134-146; src/che.cpp:36-46)
     ptp_mesh_t *h = nullptr;
     int rc;
     if constexpr (kSingle)
-        rc = ptp_mesh_create_f32((const float *) tables.GT, tables.VT, tables.OT, tables.EVT, tables.n_vertices, tables.n_half_edges, 0, &h);
+        rc = ptp_mesh_create_f32((const float *) tables.GT, tables.VT, tables.OT, tables.EVT, nv, nhe, device, &h);
     else
-        rc = ptp_mesh_create_f64((const double *) tables.GT, tables.VT, tables.OT, tables.EVT, tables.n_vertices, tables.n_half_edges, 0, &h);
+        rc = ptp_mesh_create_f64((const double *) tables.GT, tables.VT, tables.OT, tables.EVT, nv, nhe, device, &h);
     if (rc != PTP_OK) {
         fprintf(stderr, "[ptp_b200] mesh upload failed: %s\n", ptp_last_error());
         return nullptr;
     }
-    g_cache[mesh] = {h, mesh->n_vertices(), mesh->n_half_edges()};
+    g_cache[{mesh, device}] = {h, nv, nhe, tables.GT, tables.VT, tables.OT, tables.EVT, fp_gt, fp_vt, device};
     return h;
 }
 
-double solve(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> & sources, const toplesets_t & toplesets)
+double solve(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> & sources, const toplesets_t & toplesets, distance_t * dist, index_t * clusters)
 {
     ptp_mesh_t *h = resident(mesh);
     if (!h) return -1;
     ptp_stats_t st;
     int rc;
+    (void) ptp_out;
     if constexpr (kSingle)
         rc = ptp_solve_f32(h, sources.data(), (uint32_t) sources.size(), toplesets.limits.data(), (uint32_t) toplesets.limits.size(),
-                           toplesets.index, (float *) ptp_out.dist, ptp_out.clusters, NIL, &st);
+                           toplesets.index, (float *) dist, clusters, NIL, &st);
     else
         rc = ptp_solve_f64(h, sources.data(), (uint32_t) sources.size(), toplesets.limits.data(), (uint32_t) toplesets.limits.size(),
-                           toplesets.index, (double *) ptp_out.dist, ptp_out.clusters, NIL, &st);
+                           toplesets.index, (double *) dist, clusters, NIL, &st);
     if (rc != PTP_OK) {
         fprintf(stderr, "[ptp_b200] solve failed: %s\n", ptp_last_error());
         return -1;
@@ -78,15 +161,90 @@ double solve(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> &
 
 } // namespace
 
-// release the device copy of a mesh (call before the che is deleted or edited)
+// CUDA device used by the three entry points (default: PTP_B200_DEVICE or 0). Cached meshes of another device are rebuilt.
+void ptp_b200_set_device(int ordinal)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_device = ordinal < 0 ? 0 : ordinal;
+}
+
+// release the device copies of a mesh (all devices); optional — the cache validates itself on every call
 void ptp_b200_release(che * mesh)
 {
     std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_cache.find(mesh);
-    if (it != g_cache.end()) {
-        ptp_mesh_destroy(it->second.h);
-        g_cache.erase(it);
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (it->first.first == mesh) {
+            ptp_mesh_destroy(it->second.h);
+            it = g_cache.erase(it);
+        } else ++it;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Callers of the batched mode (north star: "a batched multi-source mode serves key_components, sampling and
+// distance-matrix callers"). gproshan's own loops of this shape run one `geodesics` object per point inside an OpenMP
+// loop (sampling_shape, src/sampling.cpp:16-38); here the points go to the GPUs as ONE batch.
+
+// rows[i * V + v] = geodesic distance from points[i] to v (INF if unreachable): the distance-matrix rows. Uses the first
+// n_devices CUDA devices (<= 0: all of them) through ptp_solve_batched_multi_*; the mesh is uploaded once per device.
+// Returns seconds (wall), < 0 on error.
+double distance_rows_ptp_b200(che * mesh, const std::vector<index_t> & points, distance_t * rows, int n_devices)
+{
+    if (points.empty() || !rows) return -1;
+    int avail = ptp_device_count();
+    if (avail < 1) { fprintf(stderr, "[ptp_b200] no CUDA device\n"); return -1; }
+    if (n_devices <= 0 || n_devices > avail) n_devices = avail;
+    n_devices = (int) std::min<size_t>(n_devices, points.size());
+    std::vector<ptp_mesh_t *> hs;
+    for (int d = 0; d < n_devices; d++) {
+        ptp_mesh_t *h = resident(mesh, n_devices == 1 ? -1 : d);
+        if (!h) return -1;
+        hs.push_back(h);
+    }
+    ptp_stats_t st;
+    int rc;
+    if constexpr (kSingle)
+        rc = ptp_solve_batched_multi_f32(hs.data(), n_devices, points.data(), nullptr, (uint32_t) points.size(), points.size(), (float *) rows, 0, &st);
+    else
+        rc = ptp_solve_batched_multi_f64(hs.data(), n_devices, points.data(), nullptr, (uint32_t) points.size(), points.size(), (double *) rows, 0, &st);
+    if (rc != PTP_OK) {
+        fprintf(stderr, "[ptp_b200] batched solve failed: %s\n", ptp_last_error());
+        return -1;
+    }
+    return st.ms_total / 1000;
+}
+
+// The interface of sampling_shape (src/sampling.cpp:16-38) on PTP distances: for every point, the vertices within
+// `radio` of it in order of increasing geodesic distance (ties by vertex index), its normal and the patch size.
+// Same ownership as the reference: the caller deletes indexes[i], indexes, sizes and normals.
+index_t ** sampling_shape_ptp_b200(std::vector<index_t> & points, size_t *& sizes, vertex *& normals, che * shape, size_t n_points, distance_t radio)
+{
+    const size_t n = shape->n_vertices();
+    n_points = std::min(n_points, points.size());
+    normals = new vertex[n_points];
+    sizes = new size_t[n_points];
+    index_t ** indexes = new index_t * [n_points];
+    const size_t batch = std::max<size_t>(1, std::min<size_t>(n_points, (size_t(1) << 30) / (sizeof(distance_t) * n))); // <= 1 GiB of rows at a time
+    std::vector<distance_t> rows(batch * n);
+    for (size_t first = 0; first < n_points; first += batch) {
+        const size_t nb = std::min(batch, n_points - first);
+        std::vector<index_t> src(points.begin() + first, points.begin() + first + nb);
+        const bool ok = distance_rows_ptp_b200(shape, src, rows.data(), 0) >= 0;
+        #pragma omp parallel for
+        for (size_t i = 0; i < nb; i++) {
+            const distance_t * d = rows.data() + i * n;
+            std::vector<index_t> patch;
+            if (ok)
+                for (index_t v = 0; v < n; v++)
+                    if (d[v] <= radio) patch.push_back(v);
+            std::sort(patch.begin(), patch.end(), [&](index_t a, index_t b) { return d[a] < d[b] || (d[a] == d[b] && a < b); });
+            normals[first + i] = shape->normal(points[first + i]);
+            sizes[first + i] = patch.size();
+            indexes[first + i] = new index_t[patch.size()];
+            std::copy(patch.begin(), patch.end(), indexes[first + i]);
+        }
+    }
+    return indexes;
 }
 
 // toplesets + solve on the device: what geodesics::run_parallel_toplesets_propagation_gpu (src/geodesics.cpp:225-240)
@@ -108,18 +266,34 @@ double geodesics_ptp_b200(che * mesh, const std::vector<index_t> & sources, dist
     return st.ms_total / 1000;
 }
 
-// include/geodesics_ptp.h:36
+// include/geodesics_ptp.h:36 — every entry of dist (INF for unreached vertices) and clusters is written, as the
+// reference's cudaMemcpy of the whole arrays does (src/cuda/geodesics_ptp.cu:60-75)
 double parallel_toplesets_propagation_gpu(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> & sources, const toplesets_t & toplesets)
 {
-    return solve(ptp_out, mesh, sources, toplesets);
+    return solve(ptp_out, mesh, sources, toplesets, ptp_out.dist, ptp_out.clusters);
 }
 
 // include/geodesics_ptp.h:34 — the reference rebuilds a topleset-ordered che on the CPU here (ptp_coalescence,
 // ~22 s at 10 M vertices); the library does that re-ordering on the device for every solve, so both entry points
-// share one path. set_inf is unused by the reference as well (src/cuda/geodesics_ptp_coalescence.cu:21).
+// share one path. What differs is the write-back, reproduced here: only the reached vertices — sorted[i], i <
+// limits.back() — are written, the caller's other entries are left untouched (src/cuda/geodesics_ptp_coalescence.cu:
+// 62-64, 84-86). set_inf is unused by the reference as well (:21).
 double parallel_toplesets_propagation_coalescence_gpu(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> & sources, const toplesets_t & toplesets, const bool & )
 {
-    return solve(ptp_out, mesh, sources, toplesets);
+    const size_t n = mesh->n_vertices();
+    std::vector<distance_t> dist(n);
+    std::vector<index_t> clusters(ptp_out.clusters ? n : 0);
+    const double secs = solve(ptp_out, mesh, sources, toplesets, dist.data(), ptp_out.clusters ? clusters.data() : nullptr);
+    if (secs < 0 || toplesets.limits.empty()) return secs;
+    const size_t reached = toplesets.limits.back();
+    #pragma omp parallel for
+    for (size_t i = 0; i < reached; i++) {
+        const index_t v = toplesets.index[i];
+        if (v >= n) continue;
+        ptp_out.dist[v] = dist[v];
+        if (ptp_out.clusters) ptp_out.clusters[v] = clusters[v];
+    }
+    return secs;
 }
 
 // include/geodesics_ptp.h:42

@@ -147,6 +147,20 @@ int ptp_geodesics_f64(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sour
                       double *dist, uint32_t *clusters, uint32_t cluster_fill,
                       uint32_t *sorted_index, uint64_t sorted_capacity, ptp_stats_t *stats);
 
+/* Accuracy harness: the error of the distances after each PTP iteration, as the reference's test executable records it
+ * (iter_error_run_ptp_gpu, src/cuda/test_geodesics_ptp.cu:164-211; written to <mesh>_error.iter by
+ * src/test_geodesics_ptp.cpp:198-214): for every iteration whose window already ends at the last topleset,
+ * errors[k] = compute_error(new distances, exact) = 100 / (V - S) * sum over exact > 0 of |dist - exact| / exact
+ * (src/test_geodesics_ptp.cpp:361-370) and iters[k] = the iteration number (1-based). The reference copies the whole
+ * distance array to the host after every such iteration; here the sums are formed on the device. The schedule is the
+ * solver's own (with the j/2 clamp and the iteration cap of src/geodesics_ptp.cpp:137-147, which the reference's harness
+ * loop leaves out). exact[V] are the reference distances; dist (may be NULL) receives the final distances.
+ * At most `capacity` records are written; *n_out receives their number. */
+int ptp_geodesics_error_iter_f32(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources, const float *exact, float *dist,
+                                 uint32_t *iters, float *errors, uint32_t capacity, uint32_t *n_out, ptp_stats_t *stats);
+int ptp_geodesics_error_iter_f64(ptp_mesh_t *mesh, const uint32_t *sources, uint32_t n_sources, const double *exact, double *dist,
+                                 uint32_t *iters, double *errors, uint32_t capacity, uint32_t *n_out, ptp_stats_t *stats);
+
 /* Batched independent solves (distance-matrix rows; the callers are sampling / key_components style
  * loops such as src/sampling.cpp:23-34). Source set b is sources[offsets[b] .. offsets[b+1]); with
  * offsets == NULL every source is its own single-source solve (n_batch = n_sources).
@@ -159,6 +173,20 @@ int ptp_solve_batched_f32(ptp_mesh_t *mesh, const uint32_t *sources, const uint6
 int ptp_solve_batched_f64(ptp_mesh_t *mesh, const uint32_t *sources, const uint64_t *offsets,
                           uint32_t n_batch, uint64_t n_sources, double *rows, int rows_on_device,
                           void *stream, ptp_stats_t *stats);
+
+/* The same batch over several devices of ONE process (gproshan is a single C++ process; the callers are loops such as
+ * src/sampling.cpp:23-34). meshes[0 .. n_devices) are handles of the SAME mesh created on different devices
+ * (ptp_mesh_create_* with different `device`). Source sets are block-partitioned over the devices (the first
+ * n_batch % n_devices devices take one more), one host thread per device runs its shard. rows receives all n_batch rows:
+ *   rows_on_device == 0: a host pointer; every device copies its rows straight into place (no collective);
+ *   rows_on_device != 0: a device pointer on meshes[0]'s device; the other devices' rows travel there over NVLink with
+ *     NCCL (grouped ncclSend / ncclRecv; libnccl.so.2 is loaded at run time), each shard in `gather_chunks` pieces
+ *     (ptp_set_option) so that the transfer of a piece overlaps the solving of the next.
+ * stats: counters summed over the devices; ms_solve = kernel time of the slowest device, ms_total = WALL time of the call. */
+int ptp_solve_batched_multi_f32(ptp_mesh_t *const *meshes, int n_devices, const uint32_t *sources, const uint64_t *offsets,
+                                uint32_t n_batch, uint64_t n_sources, float *rows, int rows_on_device, ptp_stats_t *stats);
+int ptp_solve_batched_multi_f64(ptp_mesh_t *const *meshes, int n_devices, const uint32_t *sources, const uint64_t *offsets,
+                                uint32_t n_batch, uint64_t n_sources, double *rows, int rows_on_device, ptp_stats_t *stats);
 
 /* Farthest-point sampling on the resident mesh. Replaces farthest_point_sampling_ptp_gpu
  * (src/cuda/geodesics_ptp.cu:87-172): starting from samples[0..n_initial), repeatedly solve from all

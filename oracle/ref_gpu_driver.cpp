@@ -8,13 +8,29 @@
 //   parallel_toplesets_propagation_gpu              src/cuda/geodesics_ptp.cu:20-85
 //   parallel_toplesets_propagation_coalescence_gpu  src/cuda/geodesics_ptp_coalescence.cu:21-100
 //   farthest_point_sampling_ptp_gpu                 src/cuda/geodesics_ptp.cu:87-172
+//   iter_error_parallel_toplesets_propagation_gpu   src/cuda/test_geodesics_ptp.cu:20-70 (its harness loop :164-211)
 // The mesh handle is the `che *` made by ref_driver.cpp (linked into the same library).
 
 #include "geodesics_ptp.h"
+#include "test_geodesics_ptp.h"
 
+#include <cmath>
 #include <vector>
 
 using namespace gproshan;
+
+// src/cuda/test_geodesics_ptp.cu calls compute_error, which the reference defines in src/test_geodesics_ptp.cpp:361-370
+// — a file that cannot be built here (it pulls in the heat method: CHOLMOD). Its eight lines are restated for the link.
+namespace gproshan {
+distance_t compute_error(const distance_t * dist, const distance_t * exact, const size_t & n, const size_t & s)
+{
+	distance_t error = 0;
+	#pragma omp parallel for reduction(+: error)
+	for(index_t v = 0; v < n; v++)
+		if(exact[v] > 0) error += std::abs(dist[v] - exact[v]) / exact[v];
+	return error * 100 / (n - s);
+}
+} // namespace gproshan
 
 extern "C" {
 
@@ -49,6 +65,20 @@ unsigned ref_fps_gpu(void * m_, unsigned * samples_io, unsigned n_in, unsigned n
 	*max_dist = farthest_point_sampling_ptp_gpu(m, s, *seconds, n, radio);
 	for(size_t i = 0; i < s.size(); i++) samples_io[i] = s[i];
 	return (unsigned) s.size();
+}
+
+// per-iteration error of the reference's harness; returns the number of (iteration, error) records written
+unsigned ref_iter_error_gpu(void * m_, const unsigned * sources, unsigned n_sources, const unsigned * limits, unsigned n_limits,
+				const unsigned * sorted, const real_t * exact, unsigned * iters, real_t * errors, unsigned cap)
+{
+	che * m = (che *) m_;
+	std::vector<index_t> src(sources, sources + n_sources);
+	std::vector<index_t> lim(limits, limits + n_limits);
+	double t;
+	std::vector<std::pair<index_t, distance_t> > r = iter_error_parallel_toplesets_propagation_gpu(m, src, lim, sorted, exact, t);
+	unsigned n = 0;
+	for(; n < r.size() && n < cap; n++) { iters[n] = r[n].first; errors[n] = r[n].second; }
+	return n;
 }
 
 } // extern "C"

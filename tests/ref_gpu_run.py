@@ -5,6 +5,7 @@ src/cuda/geodesics_ptp*.cu compiled unmodified for sm_100a) in a process of its 
 
     python tests/ref_gpu_run.py clusters <f32|f64> <out.npz>      multi-source solve with Voronoi labels
     python tests/ref_gpu_run.py fps <f32|f64> <n> <radio> <out.npz>  farthest_point_sampling_ptp_gpu
+    python tests/ref_gpu_run.py iter_error <f32|f64> <out.npz>    iter_error_parallel_toplesets_propagation_gpu (harness)
 The meshes are the seeded ones of `case_mesh` below (the test rebuilds the same)."""
 import ctypes as C
 import os
@@ -29,6 +30,13 @@ def case_mesh(kind, dtype):
     return m, src
 
 
+def exact_sphere(mesh, source):
+    """stand-in for the `.exact` files of the reference's harness: great-circle distance on the unit sphere"""
+    P = mesh.GT.astype(np.float64)
+    u = P / np.linalg.norm(P, axis=1, keepdims=True)
+    return np.arccos(np.clip(u @ u[source], -1.0, 1.0))
+
+
 def ref_cuda_path(dtype):
     return os.path.join(ROOT, "oracle", "_ref", f"libgproshan_ref_cuda_{'f32' if np.dtype(dtype) == np.float32 else 'f64'}.so")
 
@@ -44,6 +52,8 @@ def main():
     ref.L.ref_ptp_gpu.restype = C.c_double
     ref.L.ref_fps_gpu.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_uint32, ref.ct, rp, C.POINTER(C.c_double)]
     ref.L.ref_fps_gpu.restype = C.c_uint32
+    ref.L.ref_iter_error_gpu.argtypes = [C.c_void_p, u32p, C.c_uint32, u32p, C.c_uint32, u32p, rp, u32p, rp, C.c_uint32]
+    ref.L.ref_iter_error_gpu.restype = C.c_uint32
     mesh, src = case_mesh(mode, dtype)
     rc = ref.che_raw(mesh)
     if mode == "clusters":
@@ -54,6 +64,14 @@ def main():
         ref.L.ref_ptp_gpu(rc.h, ol._p(src), src.size, ol._p(lim), lim.size, ol._p(srt), ol._p(dist, ref.ct), ol._p(cl))
         cpu = rc.ptp_cpu(src, lim, srt)
         np.savez(sys.argv[3], dist=dist, clusters=cl, cpu=cpu, sources=src)
+    elif mode == "iter_error":
+        top, srt, lim = rc.compute_toplesets(src)
+        srt = np.ascontiguousarray(srt[:rc.n_v])
+        exact = exact_sphere(mesh, int(src[0])).astype(dtype)
+        it = np.zeros(4096, dtype=np.uint32)
+        er = np.zeros(4096, dtype=dtype)
+        n = ref.L.ref_iter_error_gpu(rc.h, ol._p(src), src.size, ol._p(lim), lim.size, ol._p(srt), ol._p(exact, ref.ct), ol._p(it), ol._p(er, ref.ct), 4096)
+        np.savez(sys.argv[3], iters=it[:n].copy(), errors=er[:n].copy(), n_limits=np.array(lim.size))
     else:
         n, radio = int(sys.argv[3]), float(sys.argv[4])
         buf = np.zeros(max(n, src.size, mesh.n_vertices), dtype=np.uint32)

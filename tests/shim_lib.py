@@ -34,6 +34,16 @@ class Shim:
         L.shim_geodesics.restype = C.c_double
         L.shim_fps.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_uint32, ct, rp, C.POINTER(C.c_double)]
         L.shim_fps.restype = C.c_uint32
+        L.shim_geodesics_class.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_int, C.c_int, C.c_int, rp, u32p, u32p, rp]
+        L.shim_geodesics_class.restype = C.c_uint32
+        L.shim_che_set_vertices.argtypes = [C.c_void_p, rp]
+        L.shim_ptp_gpu_prefilled.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_int, rp, u32p]
+        L.shim_ptp_gpu_prefilled.restype = C.c_double
+        L.shim_normalize_ptp.argtypes = [rp, C.c_uint32]
+        L.shim_distance_rows.argtypes = [C.c_void_p, u32p, C.c_uint32, rp, C.c_int]
+        L.shim_distance_rows.restype = C.c_double
+        L.shim_sampling_shape.argtypes = [C.c_void_p, u32p, C.c_uint32, ct, C.POINTER(C.c_ulong), u32p, C.c_ulong]
+        L.shim_sampling_shape.restype = C.c_ulong
 
     def che(self, xyz, faces):
         xyz = np.ascontiguousarray(xyz, dtype=self.dt)
@@ -46,9 +56,9 @@ class Shim:
 
     def gpu_vs_cpu(self, h, n_v, sources, coalescence=False, clusters=False):
         src = np.ascontiguousarray(sources, dtype=np.uint32)
-        dg = np.empty(n_v, dtype=self.dt)
-        dc = np.full(n_v, np.nan, dtype=self.dt)
-        cl = np.empty(n_v, dtype=np.uint32) if clusters else None
+        dg = np.full(n_v, np.inf, dtype=self.dt)   # like geodesics::geodesics (src/geodesics.cpp:27-28): the coalescence arm
+        dc = np.full(n_v, np.nan, dtype=self.dt)   # only writes the vertices it reached
+        cl = np.zeros(n_v, dtype=np.uint32) if clusters else None
         rp = C.POINTER(self.ct)
         secs = self.L.shim_ptp_gpu_vs_cpu(h, src.ctypes.data_as(u32p), src.size, int(coalescence), dg.ctypes.data_as(rp),
                                           dc.ctypes.data_as(rp), None if cl is None else cl.ctypes.data_as(u32p))
@@ -61,3 +71,57 @@ class Shim:
         secs = self.L.shim_geodesics(h, src.ctypes.data_as(u32p), src.size, d.ctypes.data_as(C.POINTER(self.ct)), None,
                                      srt.ctypes.data_as(u32p))
         return secs, d, srt
+
+    def geodesics_class(self, h, n_v, sources, opt=None, cluster=False, external_dist=False):
+        """gproshan::geodesics(mesh, sources, opt, e_dist, cluster) -> (dist, sorted_index, clusters, n_sorted, normalized)"""
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        rp = C.POINTER(self.ct)
+        d = np.empty(n_v, dtype=self.dt)
+        dn = np.empty(n_v, dtype=self.dt)
+        srt = np.empty(n_v, dtype=np.uint32)
+        cl = np.zeros(n_v, dtype=np.uint32)
+        opt = self.L.shim_option_ptp_gpu() if opt is None else opt
+        ns = self.L.shim_geodesics_class(h, src.ctypes.data_as(u32p), src.size, opt, int(cluster), int(external_dist),
+                                         d.ctypes.data_as(rp), srt.ctypes.data_as(u32p), cl.ctypes.data_as(u32p), dn.ctypes.data_as(rp))
+        return d, srt, (cl if cluster else None), ns, dn
+
+    def set_vertices(self, h, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=self.dt)
+        self.L.shim_che_set_vertices(h, xyz.ctypes.data_as(C.POINTER(self.ct)))
+
+    def ptp_gpu_prefilled(self, h, sources, dist_io, clusters_io, coalescence):
+        src = np.ascontiguousarray(sources, dtype=np.uint32)
+        return self.L.shim_ptp_gpu_prefilled(h, src.ctypes.data_as(u32p), src.size, int(coalescence), dist_io.ctypes.data_as(C.POINTER(self.ct)),
+                                             None if clusters_io is None else clusters_io.ctypes.data_as(u32p))
+
+    def fps(self, h, samples, n, radio=0.0):
+        init = np.ascontiguousarray(samples, dtype=np.uint32)
+        buf = np.zeros(max(n, init.size) + 8, dtype=np.uint32)
+        buf[:init.size] = init
+        md, secs = self.ct(0), C.c_double(0)
+        cnt = self.L.shim_fps(h, buf.ctypes.data_as(u32p), init.size, n, self.ct(radio), C.byref(md), C.byref(secs))
+        return buf[:cnt].copy(), md.value, secs.value
+
+    def normalize_ptp(self, dist):
+        d = np.ascontiguousarray(dist, dtype=self.dt).copy()
+        self.L.shim_normalize_ptp(d.ctypes.data_as(C.POINTER(self.ct)), d.size)
+        return d
+
+    def distance_rows(self, h, n_v, points, n_devices=0):
+        p = np.ascontiguousarray(points, dtype=np.uint32)
+        rows = np.empty((p.size, n_v), dtype=self.dt)
+        secs = self.L.shim_distance_rows(h, p.ctypes.data_as(u32p), p.size, rows.ctypes.data_as(C.POINTER(self.ct)), n_devices)
+        return secs, rows
+
+    def sampling_shape(self, h, n_v, points, radio):
+        p = np.ascontiguousarray(points, dtype=np.uint32)
+        sizes = np.zeros(p.size, dtype=np.uint64)
+        flat = np.empty(p.size * n_v, dtype=np.uint32)
+        tot = self.L.shim_sampling_shape(h, p.ctypes.data_as(u32p), p.size, self.ct(radio), sizes.ctypes.data_as(C.POINTER(C.c_ulong)),
+                                         flat.ctypes.data_as(u32p), flat.size)
+        out, at = [], 0
+        for s in sizes:
+            out.append(flat[at:at + int(s)].copy())
+            at += int(s)
+        assert at == tot
+        return out

@@ -65,6 +65,6 @@ def test_report_harness(tmp_path):
                      str(tmp_path), n_test=2, fps_counts=(2, 4))
     assert 0 < res[0]["error_pct"] < 5 and 0 < res[1]["error_pct"] < 5 and res[0]["seconds"] > 0
     for f in ("ptp_results.tex", "ptp_results_double.tex", "sphere30.deg", "sphere30_toplesets.dist",
-              "sphere30_toplesets_sorted.dist", "sphere30.fps", "grid40.deg"):
+              "sphere30_toplesets_sorted.dist", "sphere30.fps", "grid40.deg", "sphere30_error.iter", "grid40_error_double.iter"):
         assert (tmp_path / f).stat().st_size > 0, f
     assert sum(int(l.split()[1]) for l in open(tmp_path / "sphere30_toplesets.dist")) == s.n_vertices

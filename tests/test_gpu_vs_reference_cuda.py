@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from gproshan_b200 import api
-from ref_gpu_run import case_mesh, ref_cuda_path
+from ref_gpu_run import case_mesh, exact_sphere, ref_cuda_path
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -81,3 +81,20 @@ def test_fps_equals_reference_cuda(dtype, tmp_path):
         assert abs(md - float(ref["max_dist"])) <= 1e-9 * md
     else:
         assert same >= n - 2, (got, ref["samples"])  # float + FMA: an arg-max tie may fall on a neighbouring vertex
+
+
+def test_error_per_iteration_equals_reference_harness(tmp_path):
+    """f4: `<mesh>_error.iter` — iter_error_parallel_toplesets_propagation_gpu (src/cuda/test_geodesics_ptp.cu:20-70, loop
+    :164-211) against ptp_geodesics_error_iter_f64 on a mesh whose schedule never meets the j/2 clamp the harness omits:
+    same iteration numbers, errors equal up to the summation order and FMA contraction of the reference's kernels."""
+    need_ref(np.float64)
+    ref = run_ref(["iter_error", "f64"], tmp_path / "it.npz")
+    mesh, src = case_mesh("iter_error", np.float64)
+    exact = exact_sphere(mesh, int(src[0]))
+    with api.DeviceMesh(mesh, 0) as dm:
+        it, er, dist = dm.error_per_iteration(src, exact)
+        d2, _, _ = dm.geodesics(src)
+    assert np.array_equal(dist, d2)                       # the measurement mode does not change the solve
+    assert it.size >= 1 and np.array_equal(it, ref["iters"]), (it, ref["iters"])
+    assert np.allclose(er, ref["errors"], rtol=1e-6, atol=0), (er, ref["errors"])
+    assert 0 < er[-1] < 5.0                               # % error against the smooth sphere

@@ -3,6 +3,8 @@
 #include "../../include/ptp_b200.h"
 #include "ptp_device.cuh"
 
+#include <cuda_profiler_api.h>
+
 #include <algorithm>
 #include <cctype>
 #include <chrono>
@@ -59,7 +61,7 @@ Option g_options[] = {
     {"geo", 0, "batched solves read the per-mesh geometry table"},
     {"elastic", 1, "one-CTA-per-solve batched kernel: idle CTAs execute ticketed chunks of running solves"},
     {"causal", 1, "batched solves skip triangles that provably cannot lower a vertex (both neighbours above it; bit-exact)"},
-    {"team", 0, "batched solves: CTAs per solve (0 = default for the mesh size, 1 = one CTA per solve)"},
+    {"team", 0, "batched solves: CTAs per solve (0 = 1 when the batch fills the chip, num_sms / batch otherwise; 1 = always one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
     {"gather_chunks", 2, "ptp_solve_batched_multi_*: each device's shard is solved in this many pieces; the NCCL transfer of a "
@@ -1455,7 +1457,13 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
     if ((rc = ensure_workspace<R>(m, S, clusters != nullptr, false))) return rc;
     for (int attempt = 0;; attempt++) {
         if ((rc = upload_sources<R>(m, sources, S))) return rc;
-        if ((rc = pipeline<R>(m, S, clusters != nullptr, cl_fill))) return rc;
+        // "profile_range": the solve as ONE profiler range, so that `ncu --replay-mode range / app-range` measures the two
+        // kernels of the default path while they run side by side (kernel replay serialises them)
+        const bool prof = opt("profile_range") != 0;
+        if (prof) { CK(cudaStreamSynchronize(m->stream)); cudaProfilerStart(); }
+        rc = pipeline<R>(m, S, clusters != nullptr, cl_fill);
+        if (prof) { cudaStreamSynchronize(m->stream); cudaProfilerStop(); }
+        if (rc) return rc;
         CK(cudaMemcpyAsync(dist, m->w_out, sizeof(R) * m->V, cudaMemcpyDeviceToHost, m->stream));
         if (clusters) CK(cudaMemcpyAsync(clusters, m->w_clout, 4 * m->V, cudaMemcpyDeviceToHost, m->stream));
         rc = fetch_ctrl(m);
@@ -1507,10 +1515,14 @@ int geodesics_impl(ptp_mesh *m, const u32 *sources, u32 S, R *dist, u32 *cluster
 }
 
 // CTAs per solve of the batched path: the "team" option, or (0) the default for this mesh
-int batch_team(const ptp_mesh *m)
+// Default (0): one CTA per solve when the batch can occupy the chip (measured on C5, 296 sources: 1 CTA per solve 263,
+// teams of 2 / 4 / 8 / 16 / 37: 204 / 202 / 186 / 157 / 109 sources/s — the team barrier and the per-level BFS barriers cost
+// more than L2 residency of the windows returns), a team of num_sms / B CTAs (at most 37) per solve when it cannot
+// (8 sources on the 2 M-vertex sphere: 60 ms with teams of 18, 172 ms with one CTA per solve + elastic helpers).
+int batch_team(const ptp_mesh *m, u32 B)
 {
     long t = opt("team");
-    if (t <= 0) t = 1;
+    if (t <= 0) t = (u64)B * 2 <= (u64)m->num_sms ? std::min<long>(37, m->num_sms / std::max<u32>(B, 1u)) : 1;
     return (int)std::max<long>(1, std::min<long>(t, m->num_sms));
 }
 
@@ -1568,7 +1580,7 @@ int error_iter_impl(ptp_mesh *m, const u32 *sources, u32 S, const R *exact, R *d
 template <class R> int ensure_batch(ptp_mesh *m, u64 max_s, u64 n_src, u64 n_off, u64 rows_elems, u32 B)
 {
     int rc;
-    const u32 team = (u32)batch_team(m);
+    const u32 team = (u32)batch_team(m, B);
     int per_sm = 0;
     if (team > 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched_teams<R, false, true>, BatchCfg<R>::BLOCK, 0));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched<R, false, true>, BatchCfg<R>::BLOCK, 0));

@@ -66,7 +66,7 @@ Option g_options[] = {
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
     {"gather_chunks", 2, "ptp_solve_batched_multi_*: each device's shard is solved in this many pieces; the NCCL transfer of a "
                          "piece to the root device runs while the next piece is being solved"},
-    {"profile_range", 0, "bracket every single solve with cudaProfilerStart/Stop (ncu --replay-mode range / app-range)"},
+    {"profile_range", 0, "bracket every single solve / batched call with cudaProfilerStart/Stop (ncu --replay-mode app-range)"},
     {"debug", 0, "print per-phase device timers to stderr"},
 };
 constexpr int N_OPTIONS = (int)(sizeof g_options / sizeof g_options[0]);
@@ -537,8 +537,9 @@ __global__ void __launch_bounds__(CLUSTER_BLOCK, 1) k_toplesets_cluster(MeshView
 
 template <class R, bool CL, bool GEO>
 __global__ void __launch_bounds__(CLUSTER_BLOCK, 1)
-k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar)
+k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out, u32 *cl_out, u32 cl_fill, u32 sent, ull *bar, u32 staged)
 {
+    extern __shared__ __align__(16) unsigned char ptp_dyn_smem[];
     TeamGrid t{bar + 64, 0, 0, gridDim.x};
     t.err = w.ctrl + C_ERROR;
     const u32 tid = t.cta() * blockDim.x + threadIdx.x, nth = t.nctas() * blockDim.x;
@@ -550,7 +551,7 @@ k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_ou
     t.sync();
     if (tid == 0) flag_store(w.ctrl + C_FILLED, 1ull);
     const u32 d = ptp_run<R, TeamGrid, CL, PTP_GRID_MAP, true, GEO>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0,
-                                                                   nullptr);
+                                                                   staged ? ptp_dyn_smem : nullptr);
     scatter_run<R, TeamGrid, CL>(t, m, w, d, dist_out, cl_out, cl_fill);
     if (blockIdx.x == 0 && threadIdx.x == 0) w.ctrl[C_TEND] = global_timer();
 }
@@ -1142,12 +1143,20 @@ template <class R> int launch_two_kernels(ptp_mesh *m, u32 S, bool cl, u32 cl_fi
     cudaLaunchAttribute at2[1];
     at2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at2[0].val.programmaticStreamSerializationAllowed = 1;
+    // window staged in shared memory ("stage" = 1): measured on C3, see profiles/README.md
+    u32 staged = (opt("stage") == 1 && PTP_GRID_MAP == 4) ? 1u : 0u;
+    const size_t smem2 = staged ? CLUSTER_BLOCK * Stage4<R>::bytes_per_thread() : 0;
+    if (staged && cudaFuncSetAttribute(fs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) {
+        cudaGetLastError();
+        staged = 0;
+    }
     cfg2.gridDim = dim3((unsigned)(m->num_sms - csize));
     cfg2.blockDim = dim3(CLUSTER_BLOCK);
+    cfg2.dynamicSmemBytes = staged ? smem2 : 0;
     cfg2.stream = m->stream;
     cfg2.attrs = at2;
     cfg2.numAttrs = 1;
-    void *a2[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar};
+    void *a2[] = {&mv, &w, &src, &S, &out, &clo, &cl_fill, &sent, &bar, &staged};
     if (cudaLaunchKernelExC(&cfg2, fs, a2) != cudaSuccess) {
         // the dependent launch was refused: the BFS kernel already in the stream gives up through its watchdog; start
         // over with a clean control block and let the caller use the one-launch kernel, now and from now on
@@ -1716,6 +1725,8 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
     u64 launches = 0;
     const u32 team = m->bt_team;
+    const bool prof = opt("profile_range") != 0; // the whole batch as one profiler range (ncu --replay-mode app-range)
+    if (prof) { CK(cudaStreamSynchronize(stream)); cudaProfilerStart(); }
     for (u64 first = 0; first < B; first += chunk) {
         const u32 nb = (u32)std::min<u64>(chunk, B - first);
         R *dst = on_device ? rows + first * m->V : (R *)m->bt_rows;
@@ -1758,6 +1769,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     ull tot[16];
     CK(cudaMemcpyAsync(tot, queue, 128, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    if (prof) cudaProfilerStop();
     if (tot[10]) {
         static const char *what[] = {"", "grid barrier", "sweep team waiting for toplesets / rows", "layout warp waiting for the BFS",
                                      "layout warp waiting for its turn to publish", "BFS cluster waiting for its tables", "elastic relax chunks"};

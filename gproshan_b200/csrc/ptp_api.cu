@@ -734,7 +734,7 @@ struct ptp_mesh {
     // single-solve workspace (lazy)
     u64 ws_scap = 0; // source capacity the workspace was sized for (0 = not allocated)
     bool ws_cl = false, ws_top = false;
-    std::vector<void *> ws_allocs;
+    std::vector<std::pair<void *, size_t>> ws_allocs; // (pointer, bytes): `bytes` below is what is currently held
     void *w_key = nullptr, *w_sorted = nullptr, *w_inv = nullptr, *w_limits = nullptr, *w_tile = nullptr, *w_posS = nullptr,
          *w_ringS = nullptr, *w_ovfS = nullptr, *w_dist[2] = {nullptr, nullptr}, *w_cl[2] = {nullptr, nullptr},
          *w_top = nullptr, *w_ctrl = nullptr, *w_bar = nullptr, *w_src = nullptr, *w_out = nullptr, *w_clout = nullptr,
@@ -746,7 +746,7 @@ struct ptp_mesh {
     u32 bt_team = 0;   // CTAs per solve they were laid out for (1 = one CTA per solve)
     u32 bt_grid = 0;   // CTAs of a batched launch
     u64 bt_scap = 0;
-    std::vector<void *> bt_allocs;
+    std::vector<std::pair<void *, size_t>> bt_allocs;
     void *bt_works = nullptr, *bt_queue = nullptr, *bt_src = nullptr, *bt_off = nullptr, *bt_rows = nullptr, *bt_help = nullptr,
          *bt_bars = nullptr, *bt_ctrl = nullptr;
     u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
@@ -760,21 +760,23 @@ struct ptp_mesh {
 
 namespace {
 
-int dev_alloc(ptp_mesh *m, void **p, size_t bytes, std::vector<void *> *track)
+int dev_alloc(ptp_mesh *m, void **p, size_t bytes, std::vector<std::pair<void *, size_t>> *track)
 {
     *p = nullptr;
     if (bytes == 0) bytes = 16;
     CK(cudaMalloc(p, bytes));
     m->bytes += bytes;
-    if (track) track->push_back(*p);
+    if (track) track->push_back({*p, bytes});
     return PTP_OK;
 }
 
-void free_list(ptp_mesh *m, std::vector<void *> &l)
+void free_list(ptp_mesh *m, std::vector<std::pair<void *, size_t>> &l)
 {
-    for (void *p : l) cudaFree(p);
+    for (auto &a : l) {
+        cudaFree(a.first);
+        m->bytes -= std::min<u64>(m->bytes, a.second);
+    }
     l.clear();
-    (void)m;
 }
 
 template <class R> MeshView<R> mesh_view(const ptp_mesh *m)
@@ -820,8 +822,7 @@ template <class R> int ensure_workspace(ptp_mesh *m, u64 S, bool need_cl, bool n
     if (m->ws_scap >= S && m->ws_scap != 0 && (!need_cl || m->ws_cl) && (!need_top || m->ws_top)) return PTP_OK;
     const u64 scap = std::max<u64>(std::max<u64>(S, m->ws_scap), 1024);
     const bool cl = need_cl || m->ws_cl, top = need_top || m->ws_top;
-    for (void *p : m->ws_allocs) cudaFree(p);
-    m->ws_allocs.clear();
+    free_list(m, m->ws_allocs);
     m->ws_scap = 0;
     const u64 V = m->V, N = V + scap;
     int rc;
@@ -2254,8 +2255,8 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    for (void *p : m->ws_allocs) cudaFree(p);
-    for (void *p : m->bt_allocs) cudaFree(p);
+    free_list(m, m->ws_allocs);
+    free_list(m, m->bt_allocs);
     cudaFree(m->GT4);
     cudaFree(m->ring8);
     cudaFree(m->ovf);

@@ -48,7 +48,7 @@ int fail(int code, const std::string &msg)
 
 // Behaviour switches (ptp_set_option / ptp_get_option, include/ptp_b200.h). Each starts from the environment variable
 // PTP_<NAME IN CAPITALS> when it is set (read once, at the first use of the library) and can be changed at any time
-// through the API; the library never calls getenv() anywhere else.
+// through the API; the library reads the environment nowhere else.
 struct Option { const char *name; long value; const char *doc; };
 Option g_options[] = {
     {"fused", 5, "single solve: 5 BFS-cluster kernel + sweep kernel side by side (falls back to 4), 4 the same two teams in one "

@@ -24,6 +24,9 @@ def case_mesh(kind, dtype):
     if kind == "clusters":
         m = mg.icosphere(48, noise_sigma=4e-3, seed=77, dtype=dtype)       # 23 042 vertices, irregular: no exact ties
         src = mg.random_sources(11, 9, m.n_vertices, unique=True)
+    elif os.environ.get("REF_FPS_F"):  # timing runs (tools/run_fps.py --ref): the plain icosphere of that frequency, sample 0 first
+        m = mg.icosphere(int(os.environ["REF_FPS_F"]), dtype=dtype)
+        src = np.array([0], dtype=np.uint32)
     else:
         m = mg.icosphere(30, noise_sigma=3e-3, seed=5, dtype=dtype)
         src = np.array([17], dtype=np.uint32)

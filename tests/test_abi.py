@@ -64,3 +64,18 @@ def test_reference_gpu_leg_degrades_without_a_gpu():
         pass
     r = bench.reference_gpu_leg("c3", True, 1, False)
     assert isinstance(r, dict) and "unavailable" in r
+
+
+def test_option_table_is_documented_and_settable():
+    """ptp_set_option / ptp_get_option / ptp_option_name / ptp_option_doc: one table, no hidden getenv switches."""
+    opts = api.options()
+    for name in ("fused", "stage", "cluster", "geo", "elastic", "causal", "team", "newest", "gather_chunks", "profile_range"):
+        assert name in opts and len(opts[name][1]) > 10, name
+    old = api.get_option("gather_chunks")
+    api.set_option("gather_chunks", 5)
+    assert api.get_option("gather_chunks") == 5
+    api.set_option("gather_chunks", old)
+    with pytest.raises(api.PtpError):
+        api.set_option("no_such_option", 1)
+    src = open(os.path.join(ROOT, "gproshan_b200", "csrc", "ptp_api.cu")).read()
+    assert src.count("getenv(") == 1, "the option table is the only place that reads the environment"

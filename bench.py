@@ -315,22 +315,49 @@ def run_b200(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = n_total / (ms_step / 1e3)
 
-    # e2e: host sources in, the assembled n_total x V matrix out in pinned HOST memory, every step.
-    #   N = 1: the C-ABI call with host pointers (H2D of the sources, D2H of the rows inside the call).
-    #   N > 1: every rank solves its shard (sources from the host), the rows are gathered with NCCL and rank 0 copies the
-    #          assembled matrix to its pinned host buffer: the step ends when that copy has landed.
+    # e2e: host sources in, the assembled n_total x V matrix out in HOST memory on rank 0, every step.
+    #   N = 1: the C-ABI call with host pointers (H2D of the sources, D2H of the rows inside the call), pinned rows.
+    #   N > 1: the matrix lives in a shared-memory host buffer (/dev/shm, mapped by every rank, each rank's slice pinned);
+    #          every rank makes the same C-ABI call with a host pointer to ITS slice, so each GPU copies its rows over its
+    #          own PCIe link and the assembled matrix is complete on the host when the last rank's call returns. No
+    #          collective on this path (the NCCL gather is part of `value`, where the matrix stays on the GPUs). If the shared
+    #          buffer cannot be set up: per-rank solve, NCCL all_gather, rank 0 copies the assembled matrix to its host.
     e2e_steps = max(1, min(args.steps, 3))
-    host_rows = torch.empty((n_total, V), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    lo = rank * per_gpu
+    shared, mine_slice, shm_path, e2e_mode = None, None, None, "single"
+    if world > 1:
+        shm_path = f"/dev/shm/ptp_b200_rows_{os.environ.get('MASTER_PORT', '0')}"
+        ok = torch.zeros(1, device="cuda")
+        try:
+            if rank == 0:
+                with open(shm_path, "wb") as f:
+                    f.truncate(n_total * V * 4)
+            dist.barrier()
+            shared = torch.from_file(shm_path, shared=True, size=n_total * V, dtype=torch.float32).view(n_total, V)
+            mine_slice = shared[lo:lo + per_gpu]
+            rc = torch.cuda.cudart().cudaHostRegister(mine_slice.data_ptr(), mine_slice.numel() * 4, 0)
+            if int(rc) != 0:
+                log(f"[bench] rank {rank}: cudaHostRegister of the shared slice failed ({rc}); rows go through pageable memory")
+            ok += 1
+        except Exception as e:  # no /dev/shm, not enough room, ...
+            log(f"[bench] rank {rank}: shared host matrix unavailable ({e!r})")
+        dist.all_reduce(ok)
+        e2e_mode = "shared-host" if int(ok.item()) == world else "nccl-then-d2h"
+    host_rows = torch.empty((n_total, V), dtype=torch.float32, pin_memory=True) if rank == 0 and e2e_mode != "shared-host" else None
 
     def step_e2e():
-        if world == 1:
+        if e2e_mode == "single":
             dm.solve_batched(mine, rows=host_rows.numpy())
-        else:
-            dm.solve_batched(mine, rows_device_ptr=rows.data_ptr(), stream=stream)
-            gather_rows(rows, world, out=gathered)
-            if rank == 0:
-                host_rows.copy_(gathered, non_blocking=True)
-            torch.cuda.synchronize()
+            return float(host_rows[0, :8].sum())
+        if e2e_mode == "shared-host":
+            dm.solve_batched(mine, rows=shared[lo:lo + per_gpu].numpy())
+            dist.barrier()  # every rank's rows have landed in the host matrix
+            return float(shared[0, :8].sum()) + float(shared[n_total - 1, :8].sum()) if rank == 0 else 0.0
+        dm.solve_batched(mine, rows_device_ptr=rows.data_ptr(), stream=stream)
+        gather_rows(rows, world, out=gathered)
+        if rank == 0:
+            host_rows.copy_(gathered, non_blocking=True)
+        torch.cuda.synchronize()
         return float(host_rows[0, :8].sum()) if rank == 0 else 0.0
 
     step_e2e()
@@ -346,6 +373,28 @@ def run_b200(args, rank, world, local_rank):
     if dist:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = n_total * e2e_steps / float(e2e_s.item())
+    e2e_what = {"single": "C-ABI call, host sources in, pinned host rows out",
+                "shared-host": "per rank: the C-ABI call with host pointers — sources in, its slice of ONE shared host matrix (mapped by all ranks, "
+                               "owned by rank 0) out over its own PCIe link; no collective on this path (the NCCL gather is in `value`)",
+                "nccl-then-d2h": "per rank: host sources in, rows on device; NCCL all_gather; rank 0 copies the assembled matrix to pinned host memory"}[e2e_mode]
+    if shared is not None:
+        e2e_parity = None
+        if rank == 0:  # the assembled host matrix against the device-resident gathered one of the timed steps
+            e2e_parity = bool(torch.equal(shared[:64], gathered[:64].cpu())) and bool(torch.equal(shared[-64:], gathered[-64:].cpu()))
+        try:
+            torch.cuda.cudart().cudaHostUnregister(shared[lo:lo + per_gpu].data_ptr())
+        except Exception:
+            pass
+        mine_slice = None
+        shared = None
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
+    else:
+        e2e_parity = None
 
     kernel_ms = statistics.mean(kern_ms)
     kernel = dm.last_kernel
@@ -359,8 +408,7 @@ def run_b200(args, rank, world, local_rank):
         "vertex_updates_per_s": float(upd.item()) / (ms_step / 1e3),
         "e2e": {"value": e2e_val, "unit": "sources/s", "h2d_bytes_per_step": int(mine.nbytes) * world,
                 "d2h_bytes_per_step": int(n_total) * V * 4, "steps": e2e_steps, "checksum": checksum,
-                "what": ("C-ABI call, host sources in, pinned host rows out" if world == 1 else
-                         "per rank: host sources in, rows on device; NCCL all_gather; rank 0 copies the assembled matrix to pinned host memory")},
+                "what": e2e_what, "host_matrix_equals_gathered": e2e_parity},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("c5_batched_f32"), "peak_source": peak_src,

@@ -64,6 +64,7 @@ Option g_options[] = {
     {"team", 0, "batched solves: CTAs per solve (0 = 1 when the batch fills the chip, num_sms / batch otherwise; 1 = always one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
+    {"stream_rows", 1, "batched solves into HOST rows: copy finished rows to the host while the kernel is still solving the rest"},
     {"gather_chunks", 2, "ptp_solve_batched_multi_*: each device's shard is solved in this many pieces; the NCCL transfer of a "
                          "piece to the root device runs while the next piece is being solved"},
     {"profile_range", 0, "bracket every single solve / batched call with cudaProfilerStart/Stop (ncu --replay-mode app-range)"},
@@ -560,7 +561,8 @@ k_sweep_streamed(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_ou
 template <class R, bool GEO, bool CAUSAL>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK, BatchCfg<R>::MINB)
 k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
-          ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */, u32 n_slots)
+          ull *queue, ull *totals, HelpDesc *descs, u32 *counters /* [0] idle CTAs, [1] solves done */, u32 n_slots,
+          unsigned char *row_done /* optional: [B] set once row b is complete (host copies it out meanwhile) */)
 {
     __shared__ u32 s_b;
     __shared__ u32 s_wl[2];
@@ -601,6 +603,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
             atomicAdd(totals + 7, t2 - t1);
             atomicAdd(totals + 8, t3 - t2);
             if (descs) { __threadfence(); atomicAdd(counters + 1, 1u); }
+            if (row_done) { __threadfence(); *(volatile unsigned char *)(row_done + b) = 1; } // after the barrier behind the scatter
             atomicAdd(totals + 0, w.ctrl[C_ITER]);
             atomicAdd(totals + 1, w.ctrl[C_UPDATES]);
             atomicMax(totals + 2, w.ctrl[C_MAXWIN]);
@@ -623,7 +626,7 @@ k_batched(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *of
 template <class R, bool GEO, bool CAUSAL>
 __global__ void __launch_bounds__(BatchCfg<R>::BLOCK)
 k_batched_teams(MeshView<R> m, const Work<R> *works, const u32 *sources, const ull *offsets, u32 first, u32 B, R *rows, u32 sent,
-                ull *queue, ull *totals, ull *bars, u32 team_size)
+                ull *queue, ull *totals, ull *bars, u32 team_size, unsigned char *row_done)
 {
     const u32 team_id = blockIdx.x / team_size;
     TeamGrid t{bars + (size_t)team_id * 16, 0, team_id * team_size, team_size};
@@ -651,6 +654,7 @@ k_batched_teams(MeshView<R> m, const Work<R> *works, const u32 *sources, const u
         t.sync(); // every CTA's share of C_RELAXED is in; the workspace may be reused
         if (lead) {
             const ull t3 = global_timer();
+            if (row_done) { __threadfence(); *(volatile unsigned char *)(row_done + b) = 1; } // behind the team barrier after the scatter
             atomicAdd(totals + 6, t1 - t0); // per-phase device time summed over solves (ns)
             atomicAdd(totals + 7, t2 - t1);
             atomicAdd(totals + 8, t3 - t2);
@@ -752,6 +756,8 @@ struct ptp_mesh {
     u64 bt_src_cap = 0, bt_off_cap = 0, bt_rows_cap = 0;
 
     // multi-device batched solves: this device's shard of the rows before it travels to the root device, comm stream
+    void *bt_done = nullptr, *bt_hdone = nullptr; // per-row completion flags (device) and their pinned host copy
+    u64 bt_done_cap = 0;
     void *mg_rows = nullptr;
     u64 mg_rows_cap = 0;
     cudaStream_t mg_stream = nullptr;
@@ -1737,6 +1743,21 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
         const ull *d_off = offsets ? (const ull *)m->bt_off : nullptr;
         u32 first32 = (u32)first, nb32 = nb, sent = (u32)(m->V + m->bt_scap);
         ull *totals = queue + 1;
+        unsigned char *row_done = nullptr;
+        if (!on_device && opt("stream_rows") != 0 && nb >= 32) {
+            if (m->bt_done_cap < nb) {
+                cudaFree(m->bt_done);
+                if (m->bt_hdone) cudaFreeHost(m->bt_hdone);
+                m->bt_done = m->bt_hdone = nullptr;
+                m->bt_done_cap = 0;
+                CK(cudaMalloc(&m->bt_done, chunk));
+                CK(cudaHostAlloc(&m->bt_hdone, chunk, cudaHostAllocDefault));
+                m->bt_done_cap = chunk;
+            }
+            if (!m->mg_stream) CK(cudaStreamCreateWithFlags(&m->mg_stream, cudaStreamNonBlocking));
+            row_done = (unsigned char *)m->bt_done;
+            CK(cudaMemsetAsync(row_done, 0, nb, stream));
+        }
         if (team > 1) {
             // a team of CTAs per solve; the teams synchronise with software grid barriers, so every CTA must be resident:
             // cooperative launch (one CTA per SM)
@@ -1746,7 +1767,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
             CK(cudaMemsetAsync(bars, 0, 128 * (u64)m->bt_slots + 128, stream));
             void *fn = mv.geo ? (void *)k_batched_teams<R, true, false>
                               : (causal ? (void *)k_batched_teams<R, false, true> : (void *)k_batched_teams<R, false, false>);
-            void *args[] = {&mv, &works, &d_src, &d_off, &first32, &nb32, &dst, &sent, &queue, &totals, &bars, &tsz};
+            void *args[] = {&mv, &works, &d_src, &d_off, &first32, &nb32, &dst, &sent, &queue, &totals, &bars, &tsz, &row_done};
             CK(cudaLaunchCooperativeKernel(fn, dim3(teams * team), dim3(BatchCfg<R>::BLOCK), args, 0, stream));
             m->last_kernel = sizeof(R) == 8 ? "k_batched_teams<double>" : "k_batched_teams<float>";
         } else {
@@ -1758,13 +1779,44 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
             const u32 grid = elastic ? m->bt_grid : std::min<u32>(m->bt_slots, nb);
             auto kern = mv.geo ? k_batched<R, true, false> : (causal ? k_batched<R, false, true> : k_batched<R, false, false>);
             kern<<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, works, d_src, d_off, first32, nb32, dst, sent, queue, totals, descs, counters,
-                                                         m->bt_slots);
+                                                         m->bt_slots, row_done);
             CK(cudaGetLastError());
             m->last_kernel = sizeof(R) == 8 ? "k_batched<double>" : "k_batched<float>";
         }
         launches++;
-        if (!on_device)
+        if (!on_device && row_done) {
+            // Rows leave for the host while the kernel is still solving the rest: a second stream polls the completion flags
+            // and copies every finished prefix of the batch (solves finish roughly in queue order), so that only the last
+            // wave's rows are copied after the kernel has ended.
+            unsigned char *h_done = (unsigned char *)m->bt_hdone;
+            u64 copied = 0;
+            bool kernel_done = false;
+            while (copied < nb) {
+                if (!kernel_done) {
+                    if (cudaStreamQuery(stream) == cudaSuccess) kernel_done = true;
+                    else cudaGetLastError(); // cudaErrorNotReady is not an error: do not leave it behind for a later check
+                }
+                u64 upto = nb;
+                if (!kernel_done) {
+                    CK(cudaMemcpyAsync(h_done, row_done, nb, cudaMemcpyDeviceToHost, m->mg_stream));
+                    CK(cudaStreamSynchronize(m->mg_stream));
+                    upto = copied;
+                    while (upto < nb && h_done[upto]) upto++;
+                }
+                // (copies of at least 16 rows, or the rest: each copy costs a launch)
+                if (upto > copied && (kernel_done || upto - copied >= 16 || upto == nb)) {
+                    CK(cudaMemcpyAsync(rows + (first + copied) * m->V, (R *)m->bt_rows + copied * m->V, sizeof(R) * (upto - copied) * m->V,
+                                       cudaMemcpyDeviceToHost, m->mg_stream));
+                    copied = upto;
+                } else if (!kernel_done) {
+                    std::this_thread::sleep_for(std::chrono::microseconds(300));
+                }
+            }
+            CK(cudaStreamSynchronize(stream));      // a launch failure surfaces here
+            CK(cudaStreamSynchronize(m->mg_stream)); // the staging buffer is reused by the next chunk
+        } else if (!on_device) {
             CK(cudaMemcpyAsync(rows + first * m->V, m->bt_rows, sizeof(R) * (u64)nb * m->V, cudaMemcpyDeviceToHost, stream));
+        }
     }
     CK(cudaEventRecord(m->ev[1], stream));
     ull tot[16];
@@ -2263,6 +2315,8 @@ void ptp_mesh_destroy(ptp_mesh_t *m)
     cudaFree(m->geo);
     cudaFree(m->safe8);
     cudaFree(m->mg_rows);
+    cudaFree(m->bt_done);
+    if (m->bt_hdone) cudaFreeHost(m->bt_hdone);
     if (m->mg_stream) cudaStreamDestroy(m->mg_stream);
     if (m->mg_ev) cudaEventDestroy(m->mg_ev);
     if (m->h_ctrl) cudaFreeHost(m->h_ctrl);

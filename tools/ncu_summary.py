@@ -51,3 +51,22 @@ print("== hottest instructions (samples, executed, SASS, stalls)")
 for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:ntop]:
     st = " ".join(f"{s[6:]}={r[ix[s]]}" for s in stalls if r[ix[s]] not in ("0", ""))
     print(f"  {r[ix['# Samples']]:>8s} {r[ix['Instructions Executed']]:>11s}  {r[ix['Source']].strip()[:70]:70s} | {st}")
+
+# dynamic opcode mix: warp-level executed instructions per opcode (and the share of thread-level work)
+mix, tmix = {}, {}
+iT = ix.get("Thread Instructions Executed")
+for r in data:
+    op = r[ix["Source"]].strip().split()
+    if not op:
+        continue
+    o = op[1] if op[0].startswith("@") and len(op) > 1 else op[0]
+    o = o.split(".")[0]
+    n = int(r[ix["Instructions Executed"]] or 0)
+    mix[o] = mix.get(o, 0) + n
+    if iT is not None:
+        tmix[o] = tmix.get(o, 0) + int(r[iT] or 0)
+tot = sum(mix.values()) or 1
+print(f"== opcode mix ({tot} warp instructions)")
+for o, n in sorted(mix.items(), key=lambda x: -x[1])[:28]:
+    extra = f"  lanes/inst {tmix[o] / n:5.1f}" if iT is not None and n else ""
+    print(f"  {o:12s} {100 * n / tot:5.1f}%{extra}")

@@ -181,7 +181,7 @@ int ptp_solve_batched_f64(ptp_mesh_t *mesh, const uint32_t *sources, const uint6
  *   rows_on_device == 0: a host pointer; every device copies its rows straight into place (no collective);
  *   rows_on_device != 0: a device pointer on meshes[0]'s device; the other devices' rows travel there over NVLink with
  *     NCCL (grouped ncclSend / ncclRecv; libnccl.so.2 is loaded at run time), each shard in `gather_chunks` pieces
- *     (ptp_set_option) so that the transfer of a piece overlaps the solving of the next.
+ *     (ptp_set_option; default: one piece per two waves of CTAs) so that the transfer of a piece overlaps the solving of the next.
  * stats: counters summed over the devices; ms_solve = kernel time of the slowest device, ms_total = WALL time of the call. */
 int ptp_solve_batched_multi_f32(ptp_mesh_t *const *meshes, int n_devices, const uint32_t *sources, const uint64_t *offsets,
                                 uint32_t n_batch, uint64_t n_sources, float *rows, int rows_on_device, ptp_stats_t *stats);

@@ -39,14 +39,14 @@ def test_multi_device_rows_nccl_gather(setup):
     n_dev, mesh, srcs, want = setup
     meshes = [api.DeviceMesh(mesh, d) for d in range(n_dev)]
     try:
-        for chunks in (1, 3):
+        for chunks in (0, 1, 3):
             api.set_option("gather_chunks", chunks)
             rows = torch.zeros((srcs.size, mesh.n_vertices), dtype=torch.float32, device="cuda:0")
             api.solve_batched_multi(meshes, srcs, rows_device_ptr=rows.data_ptr())
             torch.cuda.synchronize()
             assert np.array_equal(rows.cpu().numpy(), want), f"gather_chunks={chunks}"
     finally:
-        api.set_option("gather_chunks", 2)
+        api.set_option("gather_chunks", 0)
         for m in meshes:
             m.close()
 

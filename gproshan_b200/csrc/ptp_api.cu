@@ -64,6 +64,8 @@ Option g_options[] = {
     {"team", 0, "batched solves: CTAs per solve (0 = 1 when the batch fills the chip, num_sms / batch otherwise; 1 = always one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
+    {"rows_chunk_mb", 8192, "batched solves into HOST rows: size of the device staging buffer; a batch whose rows exceed it is solved in "
+                            "several launches"},
     {"stream_rows", 1, "batched solves into HOST rows: copy finished rows to the host while the kernel is still solving the rest"},
     {"gather_chunks", 0, "ptp_solve_batched_multi_*: each device's shard is solved in this many pieces; the NCCL transfer of a "
                          "piece to the root device runs while the next piece is being solved (0 = one piece per two waves of CTAs, "
@@ -1708,7 +1710,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     // host rows: stage through a device buffer of at most ~8 GiB, chunk by chunk
     u64 chunk = B;
     if (!on_device) {
-        const u64 budget = 8ull << 30;
+        const u64 budget = (u64)std::max<long>(1, opt("rows_chunk_mb")) << 20;
         chunk = std::max<u64>(1, std::min<u64>(B, budget / (sizeof(R) * m->V)));
     }
     if ((rc = ensure_batch<R>(m, max_s, n_src, offsets ? B + 1 : 0, on_device ? 0 : chunk * m->V, B))) return rc;

@@ -161,6 +161,8 @@ double solve(const ptp_out_t & ptp_out, che * mesh, const std::vector<index_t> &
 
 } // namespace
 
+double geodesics_ptp_b200(che * mesh, const std::vector<index_t> & sources, distance_t * dist, index_t * clusters, index_t * sorted_index);
+
 // CUDA device used by the three entry points (default: PTP_B200_DEVICE or 0). Cached meshes of another device are rebuilt.
 void ptp_b200_set_device(int ordinal)
 {
@@ -245,6 +247,49 @@ index_t ** sampling_shape_ptp_b200(std::vector<index_t> & points, size_t *& size
         }
     }
     return indexes;
+}
+
+// key_components::compute_kcs (src/key_components.cpp:51-63) on the new engine. The reference builds its key components from
+// a fast-marching `geodesics` object (sorted order + radio()), which PTP does not provide (n_sorted stays 0); the same
+// construction on PTP distances: ONE multi-source solve from the key points on the GPU, then — on the host, as in the
+// reference — the vertices are visited by increasing distance (ties by index) while dist <= radio_fraction * (largest
+// finite distance) and joined with their star neighbours (union-find with the reference's join rule: the visited vertex's
+// root absorbs the neighbour's); roots of components larger than one vertex are numbered in vertex order.
+// comp_out[v] = component number or NIL (the value key_components::operator() returns); returns the number of components.
+size_t key_components_ptp_b200(che * mesh, const std::vector<index_t> & key_points, real_t radio_fraction, index_t * comp_out)
+{
+    const size_t n = mesh->n_vertices();
+    std::vector<distance_t> dist(n, INFINITY);
+    if (geodesics_ptp_b200(mesh, key_points, dist.data(), nullptr, nullptr) < 0) return 0;
+    distance_t max_d = 0;
+    for (size_t v = 0; v < n; v++)
+        if (dist[v] < INFINITY && dist[v] > max_d) max_d = dist[v];
+    const distance_t radio = radio_fraction * max_d;
+    std::vector<index_t> order(n), comp(n);
+    std::vector<size_t> comp_size(n, 1);
+    std::iota(order.begin(), order.end(), 0);
+    std::iota(comp.begin(), comp.end(), 0);
+    std::sort(order.begin(), order.end(), [&](index_t a, index_t b) { return dist[a] < dist[b] || (dist[a] == dist[b] && a < b); });
+    auto find = [&](index_t x) {
+        while (comp[x] != x) { comp[x] = comp[comp[x]]; x = comp[x]; }
+        return x;
+    };
+    for (size_t i = 0; i < n && dist[order[i]] <= radio; i++) {
+        const index_t v = order[i];
+        for_star(he, mesh, v) {
+            const index_t x = find(v), y = find(mesh->vt(next(he)));
+            if (x != y) { comp_size[x] += comp_size[y]; comp[y] = x; }
+        }
+    }
+    std::vector<index_t> number(n, NIL);
+    size_t n_comp = 0;
+    for (index_t i = 0; i < n; i++)
+        if (comp[i] == i && comp_size[i] > 1) number[i] = (index_t) n_comp++;
+    for (index_t i = 0; i < n; i++) {
+        const index_t r = find(i);
+        comp_out[i] = (r == i && comp_size[i] <= 1) ? NIL : number[r];
+    }
+    return n_comp;
 }
 
 // toplesets + solve on the device: what geodesics::run_parallel_toplesets_propagation_gpu (src/geodesics.cpp:225-240)

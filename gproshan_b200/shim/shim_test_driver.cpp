@@ -10,6 +10,7 @@ using namespace gproshan;
 
 namespace gproshan {
 void ptp_b200_release(che * mesh);
+size_t key_components_ptp_b200(che * mesh, const std::vector<index_t> & key_points, real_t radio_fraction, index_t * comp_out);
 double distance_rows_ptp_b200(che * mesh, const std::vector<index_t> & points, distance_t * rows, int n_devices);
 index_t ** sampling_shape_ptp_b200(std::vector<index_t> & points, size_t *& sizes, vertex *& normals, che * shape, size_t n_points, distance_t radio);
 double geodesics_ptp_b200(che * mesh, const std::vector<index_t> & sources, distance_t * dist, index_t * clusters, index_t * sorted_index);
@@ -137,6 +138,12 @@ unsigned long shim_sampling_shape(void * m_, const unsigned * points, unsigned n
     delete [] sizes;
     delete [] normals;
     return total;
+}
+
+unsigned long shim_key_components(void * m_, const unsigned * kps, unsigned n_kps, real_t radio_fraction, unsigned * comp_out)
+{
+    std::vector<index_t> k(kps, kps + n_kps);
+    return key_components_ptp_b200((che *) m_, k, radio_fraction, comp_out);
 }
 
 int shim_option_ptp_gpu() { return (int) geodesics::PTP_GPU; }

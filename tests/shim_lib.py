@@ -44,6 +44,8 @@ class Shim:
         L.shim_distance_rows.restype = C.c_double
         L.shim_sampling_shape.argtypes = [C.c_void_p, u32p, C.c_uint32, ct, C.POINTER(C.c_ulong), u32p, C.c_ulong]
         L.shim_sampling_shape.restype = C.c_ulong
+        L.shim_key_components.argtypes = [C.c_void_p, u32p, C.c_uint32, ct, u32p]
+        L.shim_key_components.restype = C.c_ulong
 
     def che(self, xyz, faces):
         xyz = np.ascontiguousarray(xyz, dtype=self.dt)
@@ -125,3 +127,9 @@ class Shim:
             at += int(s)
         assert at == tot
         return out
+
+    def key_components(self, h, n_v, key_points, radio_fraction):
+        k = np.ascontiguousarray(key_points, dtype=np.uint32)
+        comp = np.empty(n_v, dtype=np.uint32)
+        n = self.L.shim_key_components(h, k.ctypes.data_as(u32p), k.size, self.ct(radio_fraction), comp.ctypes.data_as(u32p))
+        return int(n), comp

@@ -142,6 +142,31 @@ def test_wide_windows_batched(dtype, oracle, gpu):
         assert_dist_parity(rows[b], want, dtype, f"row {b}")
 
 
+def test_batched_host_rows_in_several_launches(oracle, gpu):
+    """host rows larger than the device staging buffer: several launches, each streaming its finished rows to the host
+    while it runs (`stream_rows`), against one launch with the rows assembled on the device"""
+    import torch
+    m = mg.icosphere(16, 2e-3, seed=11).astype(np.float32)
+    srcs = mg.random_sources(5, 150, m.n_vertices, unique=True)
+    dev = torch.empty((srcs.size, m.n_vertices), dtype=torch.float32, device="cuda")
+    try:
+        api.set_option("rows_chunk_mb", 1)     # 1 MiB / (4 B x 2 562 vertices) = 102 rows per launch
+        with api.DeviceMesh(m, gpu) as dm:
+            dm.solve_batched(srcs, rows_device_ptr=dev.data_ptr())
+            want = dev.cpu().numpy()
+            got = dm.solve_batched(srcs)
+            assert dm.last_stats["gpu_launches"] == 2
+            api.set_option("stream_rows", 0)
+            got_plain = dm.solve_batched(srcs)
+    finally:
+        api.set_option("rows_chunk_mb", 8192)
+        api.set_option("stream_rows", 1)
+    assert np.array_equal(got, want) and np.array_equal(got_plain, want)
+    assert srcs.size > 102 + 32    # two launches, the second still large enough to stream
+    t0, s0, l0 = oracle.compute_toplesets(m, [srcs[-1]])
+    assert_dist_parity(got[-1], oracle.ptp_cpu(m, [srcs[-1]], l0, s0)[0], np.float32, "last row")
+
+
 def test_batched_source_sets(oracle, gpu):
     m = mg.torus(48, 20).astype(np.float32)
     sets = [[1, 500], [77], [3, 3, 900, 20], [959]]

@@ -214,3 +214,58 @@ def test_batched_callers_distance_rows_and_sampling_shape(dtype, oracle):
             assert patches[k][0] == pts[k]
     finally:
         sh.destroy(h)
+
+
+@needs_shim
+@pytest.mark.gpu
+def test_key_components_on_ptp_distances(oracle):
+    """key_components::compute_kcs (src/key_components.cpp:51-63) routed onto the GPU solve: against the same construction in
+    numpy on the reference's CPU PTP distances (star order from the CHE tables)."""
+    from gproshan_b200 import meshgen as mg
+    dtype = np.float64
+    mesh = mg.icosphere(14, 3e-3, seed=9).astype(dtype)
+    kps = mg.random_sources(21, 6, mesh.n_vertices, unique=True)
+    frac = 0.18
+    sh = Shim(dtype)
+    h, n_v = sh.che(mesh.GT, mesh.VT)
+    try:
+        n_comp, comp = sh.key_components(h, n_v, kps, frac)
+        _, _, dist, _ = sh.gpu_vs_cpu(h, n_v, kps)          # [2]: parallel_toplesets_propagation_cpu of the reference
+    finally:
+        sh.destroy(h)
+    VT, OT, EVT = mesh.VT, mesh.OT, mesh.EVT
+    nxt = lambda he: 3 * (he // 3) + (he + 1) % 3
+    prv = lambda he: 3 * (he // 3) + (he + 2) % 3
+    parent = np.arange(n_v)
+    size = np.ones(n_v, dtype=np.int64)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    radio = frac * dist[np.isfinite(dist)].max()
+    for v in np.lexsort((np.arange(n_v), dist)):
+        if not dist[v] <= radio:
+            break
+        he = EVT[v]
+        while he != 0xFFFFFFFF:
+            x, y = find(v), find(VT[nxt(he)])
+            if x != y:
+                size[x] += size[y]
+                parent[y] = x
+            he = OT[prv(he)]
+            if he == EVT[v]:
+                break
+    want = np.full(n_v, 0xFFFFFFFF, dtype=np.uint32)
+    number, k = {}, 0
+    for i in range(n_v):
+        if parent[i] == i and size[i] > 1:
+            number[i] = k
+            k += 1
+    for i in range(n_v):
+        r = find(i)
+        if r in number:
+            want[i] = number[r]
+    assert n_comp == k and 1 <= k <= len(kps)
+    assert np.array_equal(comp, want)

@@ -97,6 +97,10 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """the timed region starts here: only samples taken from now on are reported"""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -104,7 +108,7 @@ class ClockSampler:
         self.proc.terminate()
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -287,14 +291,18 @@ def run_b200(args, rank, world, local_rank):
             gather_rows(rows, world, out=gathered)
         return dm.last_stats
 
+    # (the sampler is started BEFORE the warm-up: nvidia-smi's own start-up — NVML initialisation, ~0.3 s, during which CUDA
+    # calls of this process can stall — must not fall into the timed region; only samples taken after mark() are reported)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     kern_ms, updates, launches = [], 0, 0

@@ -2,6 +2,9 @@
 // Device algorithms live in ptp_device.cuh. Build: gproshan_b200/build.py (nvcc, sm_100a, -lineinfo).
 #include "../../include/ptp_b200.h"
 #include "ptp_device.cuh"
+#ifndef PTP_MAXL1
+#define PTP_MAXL1 0
+#endif
 
 #include <cuda_profiler_api.h>
 
@@ -392,6 +395,75 @@ k_dbg_consumer(MeshView<R> m, Work<R> w, const u32 *sources, u32 S, R *dist_out,
     t.err = w.ctrl + C_ERROR;
     const u32 d = ptp_run<R, TeamGrid, false, PTP_GRID_MAP, true>(t, m, w, sources, S, 0u, 0u, sent, w.tile_sum + 2048, m.ring_symmetric != 0);
     scatter_run<R, TeamGrid, false>(t, m, w, d, dist_out, nullptr, 0u);
+}
+
+// DEBUG / verification: Ops<R>::inv_gram (three divisions sharing one reciprocal) against three plain IEEE divisions, bit for
+// bit, on (a) Gram matrices of random edge pairs at random scales, (b) raw random bit patterns and specials
+// (ptp_debug_inv_gram_check). out[0] = mismatching results, out[1] = cases that took the shared-reciprocal path.
+__device__ __forceinline__ ull dbg_mix(ull x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+template <class R> struct DbgBits;
+template <> struct DbgBits<float> {
+    static __device__ __forceinline__ float from(ull h) { return __uint_as_float((u32)h); }
+    static __device__ __forceinline__ bool same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
+    static __device__ __forceinline__ float scale(int e) { return __uint_as_float((u32)(127 + e) << 23); }
+    static constexpr int ESPAN = 30;
+};
+template <> struct DbgBits<double> {
+    static __device__ __forceinline__ double from(ull h) { return __longlong_as_double((long long)h); }
+    static __device__ __forceinline__ bool same(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b) || (a != a && b != b); }
+    static __device__ __forceinline__ double scale(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+    static constexpr int ESPAN = 500;
+};
+template <class R>
+__global__ void k_dbg_inv_gram(ull n, ull seed, ull *out, double *samples)
+{
+    typedef Ops<R> O;
+    typedef DbgBits<R> B;
+    ull bad = 0, fast = 0;
+    for (ull i = blockIdx.x * (ull)blockDim.x + threadIdx.x; i < n; i += (ull)gridDim.x * blockDim.x) {
+        ull h = dbg_mix(seed ^ (i * 0xD1342543DE82EF95ull));
+        R q00, q01, q11, det;
+        const u32 kind = (u32)(h & 7u);
+        if (kind < 5) { // Gram matrix of two random edges, common scale 2^e, relative length and angle free
+            const int e = (int)((h >> 8) % (2u * B::ESPAN + 1u)) - B::ESPAN;
+            R x[6];
+            for (int k = 0; k < 6; k++) {
+                h = dbg_mix(h);
+                x[k] = (R)((double)(long long)(h >> 11) * (1.0 / 4503599627370496.0) - 1.0) * B::scale(e);
+            }
+            if (kind == 3) { x[3] = x[0]; x[4] = x[1]; h = dbg_mix(h); x[5] = x[2] * (R)(1.0 + (double)(h & 0xffff) * 1e-7); } // nearly parallel
+            if (kind == 4) { x[3] = -x[1]; x[4] = x[0]; x[2] = 0; x[5] = 0; }                                                // right angle: q01 == 0
+            const P3<R> X0 = {x[0], x[1], x[2]}, X1 = {x[3], x[4], x[5]};
+            q00 = dot3(X0, X0); q11 = dot3(X1, X1); q01 = dot3(X0, X1);
+            det = O::sub(O::mul(q00, q11), O::mul(q01, q01));
+        } else { // raw bit patterns: every class of special operand turns up
+            q00 = B::from(dbg_mix(h + 1)); q01 = B::from(dbg_mix(h + 2)); q11 = B::from(dbg_mix(h + 3)); det = B::from(dbg_mix(h + 4));
+            if (kind == 6) { q00 = O::abs(q00); q11 = O::abs(q11); det = O::abs(det); }
+            if (kind == 7) { const u32 w = (u32)(h >> 40) & 7u; const R sp[8] = {R(0), -R(0), O::inf(), -O::inf(), O::sub(O::inf(), O::inf()), R(1), B::scale(-B::ESPAN * 2), B::scale(B::ESPAN * 2)};
+                             if (h & 0x100) q00 = sp[w]; if (h & 0x200) q01 = sp[(w + 1) & 7]; if (h & 0x400) q11 = sp[(w + 2) & 7]; if (h & 0x800) det = sp[(w + 3) & 7]; }
+        }
+        R a, b, c;
+        fast += O::inv_gram(q00, q01, q11, det, a, b, c) ? 1u : 0u;
+        const R ra = O::div(q11, det), rb = O::div(-q01, det), rc = O::div(q00, det);
+        const u32 nb = (B::same(a, ra) ? 0u : 1u) + (B::same(b, rb) ? 0u : 1u) + (B::same(c, rc) ? 0u : 1u);
+        if (nb && samples) { // the first few offenders, for diagnosis: operands and both results
+            const ull at = atomicAdd(out + 2, 1ull);
+            if (at < 16) {
+                double *sp = samples + at * 10;
+                sp[0] = (double)q00; sp[1] = (double)q01; sp[2] = (double)q11; sp[3] = (double)det;
+                sp[4] = (double)a; sp[5] = (double)ra; sp[6] = (double)b; sp[7] = (double)rb; sp[8] = (double)c; sp[9] = (double)rc;
+            }
+        }
+        bad += nb;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (fast) atomicAdd(out + 1, fast);
 }
 
 // DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
@@ -1781,6 +1853,10 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
             if (elastic) CK(cudaMemsetAsync(m->bt_help, 0, sizeof(HelpDesc) * m->bt_slots + 64, stream));
             const u32 grid = elastic ? m->bt_grid : std::min<u32>(m->bt_slots, nb);
             auto kern = mv.geo ? k_batched<R, true, false> : (causal ? k_batched<R, false, true> : k_batched<R, false, false>);
+#if PTP_MAXL1
+            // the kernel uses < 1 KB of shared memory and lives on L1 hits of its gathers: ask for the largest L1 split
+            cudaFuncSetAttribute((const void *)kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+#endif
             kern<<<grid, BatchCfg<R>::BLOCK, 0, stream>>>(mv, works, d_src, d_off, first32, nb32, dst, sent, queue, totals, descs, counters,
                                                          m->bt_slots, row_done);
             CK(cudaGetLastError());
@@ -2263,6 +2339,29 @@ int ptp_che_build(const uint32_t *VT, uint64_t V, uint64_t H, uint32_t *OT, uint
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;
+}
+
+// verification helper (not part of the reference interface): see k_dbg_inv_gram
+int ptp_debug_inv_gram_check(uint64_t n, uint64_t seed, int real_size, uint64_t *mismatches, uint64_t *shared_path, double *samples160)
+{
+    ull *out = nullptr;
+    double *smp = nullptr;
+    if (real_size != 4 && real_size != 8) return fail(PTP_ERR_INVALID, "real_size must be 4 or 8");
+    if (cudaMalloc(&out, 24) != cudaSuccess) { cudaGetLastError(); return fail(PTP_ERR_NO_DEVICE, "no CUDA device"); }
+    if (samples160 && cudaMalloc(&smp, 160 * sizeof(double)) != cudaSuccess) { cudaFree(out); return fail(PTP_ERR_CUDA, "cudaMalloc"); }
+    cudaMemset(out, 0, 24);
+    if (smp) cudaMemset(smp, 0, 160 * sizeof(double));
+    if (real_size == 4) k_dbg_inv_gram<float><<<1184, 256>>>((ull)n, (ull)seed, out, smp);
+    else k_dbg_inv_gram<double><<<1184, 256>>>((ull)n, (ull)seed, out, smp);
+    ull h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpy(h, out, 24, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && smp) e = cudaMemcpy(samples160, smp, 160 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    cudaFree(smp);
+    if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
+    if (mismatches) *mismatches = h[0];
+    if (shared_path) *shared_path = h[1];
+    return PTP_OK;
 }
 
 // measurement helper (not part of the reference interface): nanoseconds per grid barrier of `ctas` CTAs x `block` threads

@@ -203,6 +203,15 @@ int ptp_farthest_point_sampling_f64(ptp_mesh_t *mesh, uint32_t *samples, uint32_
  * ctas < 0 measures the hardware barrier of ONE thread-block cluster of -ctas CTAs instead (BFS team). */
 double ptp_debug_barrier_ns(int ctas, int block, int n);
 
+/* Verification helper, not part of the reference interface: the inverse Gram matrix of update_step
+ * (src/geodesics_ptp.cpp:212-231) is computed with ONE reciprocal shared by its three IEEE divisions; this runs that code
+ * and three plain IEEE divisions on `n` generated operand sets (Gram matrices of random edge pairs over the whole exponent
+ * range, raw bit patterns, zeros / infinities / NaNs / denormals) and counts results that differ in any bit
+ * (*mismatches, expected 0) and the sets that took the shared-reciprocal path (*shared_path). real_size = 4 | 8.
+ * samples160: NULL, or room for 16 x 10 doubles describing the first offenders (q00, q01, q11, det, then got / want x 3). */
+int ptp_debug_inv_gram_check(uint64_t n, uint64_t seed, int real_size, uint64_t *mismatches, uint64_t *shared_path,
+                             double *samples160);
+
 #ifdef __cplusplus
 }
 #endif

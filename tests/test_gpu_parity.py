@@ -333,3 +333,20 @@ def test_config_c4_shape_multi_source_voronoi(dtype, oracle, gpu):
     assert np.array_equal(g2.dist, got) and np.array_equal(g2.clusters, cl)
     # each source is its own nearest source
     assert np.array_equal(cl[src], 1 + np.array([np.nonzero(src == s)[0].max() for s in src]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real_size", [4, 8])
+def test_inv_gram_shared_reciprocal_is_ieee_division(real_size):
+    """The inverse Gram matrix of update_step (src/geodesics_ptp.cpp:212-231: q11/det, -q01/det, q00/det) is computed with
+    one reciprocal shared by the three divisions; every result must equal the plain IEEE division in every bit, over
+    Gram matrices of random edge pairs at all scales, raw bit patterns and specials — and the shared path must be the one
+    that normally runs."""
+    import ctypes as C
+    from gproshan_b200 import _lib
+    L = _lib.lib()
+    bad, fast = C.c_uint64(0), C.c_uint64(0)
+    n = 400_000_000
+    _lib.check(L.ptp_debug_inv_gram_check(n, 20261017 + real_size, real_size, C.byref(bad), C.byref(fast), None))
+    assert bad.value == 0
+    assert fast.value > n // 8  # the well-shaped geometric cases at moderate scales take the shared path

@@ -22,3 +22,6 @@ with api.DeviceMesh(mesh, 0) as dm:
         st = dm.last_stats
         print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()},
               "sources/s", round(nsrc / (st["ms_total"] / 1e3), 1), flush=True)
+    # bit-level checksum of the whole matrix: A/B builds must print the same number
+    iv = rows.view(torch.int32 if dt == np.float32 else torch.int64)
+    print("checksum", int(iv.to(torch.int64).sum().item()), int((iv.to(torch.int64) * (torch.arange(iv.shape[1], device="cuda") % 8191 + 1)).sum().item()), flush=True)

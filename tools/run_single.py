@@ -14,5 +14,6 @@ dt = np.float32 if (len(sys.argv) > 3 and sys.argv[3] == "f32") else np.float64
 mesh = mg.icosphere(f, noise_sigma=0.2 * mg.mean_edge_icosphere(f), seed=12345, dtype=dt)
 with api.DeviceMesh(mesh, 0) as dm:
     for _ in range(n):
-        dm.geodesics([0])
+        d, _, _ = dm.geodesics([0])
         print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in dm.last_stats.items()}, flush=True)
+    print("checksum", int(d.view(np.int64 if dt == np.float64 else np.int32).astype(np.int64).sum()), flush=True)  # A/B builds must agree

@@ -64,6 +64,7 @@ Option g_options[] = {
     {"geo", 0, "batched solves read the per-mesh geometry table"},
     {"elastic", 1, "one-CTA-per-solve batched kernel: idle CTAs execute ticketed chunks of running solves"},
     {"causal", 1, "batched solves skip triangles that provably cannot lower a vertex (both neighbours above it; bit-exact)"},
+    {"sign_short", 1, "batched solves (with causal) decide update_step's acceptance condition from its two-term form where provably equal (bit-exact)"},
     {"team", 0, "batched solves: CTAs per solve (0 = 1 when the batch fills the chip, num_sms / batch otherwise; 1 = always one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
@@ -271,8 +272,11 @@ __global__ void k_geo_build(const typename Ops<R>::vec4 *__restrict__ GT4, const
 
 // Causal-safe flags (MeshView::safe8): bit k of safe8[v] = the planar update on triangle k = (v, n_k, n_{k+1}) obeys the
 // bound p >= min(t0, t1)(1 - 75 u) (causal_safe in ptp_device.cuh). One thread per vertex; overflow rows get 0.
+// safe8[V + v]: the same per triangle for the short sign test of the acceptance condition (sign_short_ok; all 0 when the
+// "sign_short" option is off).
 template <class R>
-__global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, const u32 *__restrict__ ring8, u32 V, unsigned char *__restrict__ safe8)
+__global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, const u32 *__restrict__ ring8, u32 V, unsigned char *__restrict__ safe8,
+                             u32 with_sign)
 {
     typedef Ops<R> O;
     const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,7 +284,7 @@ __global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, cons
     const u32 *row = ring8 + (size_t)v * GL;
     u32 e[GL];
     for (u32 k = 0; k < GL; k++) e[k] = row[k];
-    u32 len = 0, bits = 0;
+    u32 len = 0, bits = 0, sbits = 0;
     bool open = false;
     if (e[0] != OVF && e[0] != NIL) {
         open = (e[0] & OPEN_BIT) != 0;
@@ -299,8 +303,14 @@ __global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, cons
     for (u32 k = 0; k < n_tri; k++) {
         const u32 k1 = k + 1 < len ? k + 1 : 0;
         if (causal_safe<R>(X[k], X[k1], q[k], q[k1])) bits |= 1u << k;
+        if (with_sign) {
+            const R q01 = dot3(X[k], X[k1]);
+            const R det = O::sub(O::mul(q[k], q[k1]), O::mul(q01, q01)); // as update_step computes it
+            if (sign_short_ok<R>(q[k], q[k1], det)) sbits |= 1u << k;
+        }
     }
     safe8[v] = (unsigned char)bits;
+    safe8[(size_t)V + v] = (unsigned char)sbits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,6 +474,85 @@ __global__ void k_dbg_inv_gram(ull n, ull seed, ull *out, double *samples)
     }
     if (bad) atomicAdd(out, bad);
     if (fast) atomicAdd(out + 1, fast);
+}
+
+// DEBUG / verification: the short sign test of update_step's acceptance condition (tri_front, sign_short) against the
+// reference's 43-operation chain (ptp_debug_sign_short_check). Triangles of random shape and scale (incl. shapes at the
+// edge of what sign_short_ok admits), distances around them random or ADVERSARIAL: tp chosen so that one of the two-term
+// forms nearly cancels (|e| from 2^-30 to 2^-2 of its terms). out[0] = evaluations in which the short form decided and the
+// full chain disagrees (expected 0), out[1] = evaluations decided by the short form, out[2] = evaluations of flagged triangles.
+template <class R>
+__global__ void k_dbg_sign_short(ull n, ull seed, ull *out)
+{
+    typedef Ops<R> O;
+    typedef DbgBits<R> B;
+    ull bad = 0, decided = 0, flagged = 0;
+    for (ull i = blockIdx.x * (ull)blockDim.x + threadIdx.x; i < n; i += (ull)gridDim.x * blockDim.x) {
+        ull h = dbg_mix(seed ^ (i * 0xD1342543DE82EF95ull));
+        auto unif = [&]() -> double { h = dbg_mix(h); return (double)(long long)(h >> 11) * (1.0 / 9007199254740992.0); }; // [0, 1)
+        const u32 kind = (u32)(h & 7u);
+        const int e = (int)((h >> 8) % 27u) - 13; // edge scale 2^e
+        // two edges: length ratio up to 3, angle from 12 to 168 degrees (the flag admits roughly 18..162), random frame
+        const double len0 = 1.0 + unif(), len1 = len0 * (kind & 1 ? 1.0 + 2.0 * unif() : 1.0 / (1.0 + 2.0 * unif()));
+        const double ang = (12.0 + 156.0 * unif()) * 0.017453292519943295;
+        double f0[3] = {unif() - 0.5, unif() - 0.5, unif() - 0.5}, f1[3] = {unif() - 0.5, unif() - 0.5, unif() - 0.5};
+        double n0 = sqrt(f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2]) + 1e-300;
+        for (int k = 0; k < 3; k++) f0[k] /= n0;
+        double d = f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2];
+        for (int k = 0; k < 3; k++) f1[k] -= d * f0[k];
+        double n1 = sqrt(f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2]) + 1e-300;
+        for (int k = 0; k < 3; k++) f1[k] /= n1;
+        const double sc = (double)B::scale(e);
+        P3<R> X0, X1;
+        X0.x = (R)(len0 * f0[0] * sc); X0.y = (R)(len0 * f0[1] * sc); X0.z = (R)(len0 * f0[2] * sc);
+        X1.x = (R)(len1 * (cos(ang) * f0[0] + sin(ang) * f1[0]) * sc);
+        X1.y = (R)(len1 * (cos(ang) * f0[1] + sin(ang) * f1[1]) * sc);
+        X1.z = (R)(len1 * (cos(ang) * f0[2] + sin(ang) * f1[2]) * sc);
+        const R q00 = dot3(X0, X0), q11 = dot3(X1, X1), q01 = dot3(X0, X1);
+        const R det = O::sub(O::mul(q00, q11), O::mul(q01, q01));
+        if (!sign_short_ok<R>(q00, q11, det)) continue;
+        flagged++;
+        const TriQ<R> Q = tri_geom<R>(X0, X1, q00, q11);
+        // distances: base value of random magnitude, difference of the order of the edges
+        const double base = sc * (kind < 6 ? 16.0 + 500.0 * unif() : 16.0 + 1e-3 * unif());
+        R t0 = (R)(base), t1 = (R)(base + sc * len0 * (2.0 * unif() - 1.0));
+        if (kind >= 2 && kind < 6) {
+            // adversarial: e0 = 0 is the front running along edge X1 (p = t1 + |X1|, i.e. tp1 = -|X1|, tp0 = Q01 |X1| / Q00),
+            // e1 = 0 the same along X0; the planar update only depends on t1 - t0, so the zero sits at
+            // t1 - t0 = -|X1| (1 + Q01 / Q00)  resp.  |X0| (1 + Q01 / Q11). Move off it by a relative 2^-2 ... 2^-30, or not at all.
+            const bool first = (kind & 1) != 0;
+            const u32 k = (u32)((h >> 40) % 30u);
+            const double off = k == 29 ? 0.0 : ldexp(1.0, -2 - (int)k) * ((h >> 50) & 1 ? 1.0 : -1.0);
+            const double x0 = sqrt((double)q00), x1 = sqrt((double)q11);
+            const double dz = first ? -x1 * (1.0 + (double)Q.Q01 / (double)Q.Q00) : x0 * (1.0 + (double)Q.Q01 / (double)Q.Q11);
+            t1 = (R)((double)t0 + dz * (1.0 + off));
+        }
+        if (!(t0 >= R(0)) || !(t1 >= R(0)) || !(t0 < O::inf()) || !(t1 < O::inf())) continue;
+        bool fb_full = false, fb_short = false;
+        const R pf = tri_front<R>(X0, X1, Q, t0, t1, fb_full, false);
+        const R ps = tri_front<R>(X0, X1, Q, t0, t1, fb_short, true);
+        // did the short form decide? re-evaluate its predicate (the same expressions)
+        bool dec = false;
+        {
+            const R delta = O::add(O::mul(t0, O::add(Q.Q00, Q.Q01)), O::mul(t1, O::add(Q.Q01, Q.Q11)));
+            const R sumQ = O::add(O::add(O::add(Q.Q00, Q.Q01), Q.Q01), Q.Q11);
+            const R inner = O::sub(O::add(O::add(O::mul(O::mul(t0, t0), Q.Q00), O::mul(O::mul(t0, t1), O::add(Q.Q01, Q.Q01))), O::mul(O::mul(t1, t1), Q.Q11)), R(1));
+            const R dis = O::sub(O::mul(delta, delta), O::mul(sumQ, inner));
+            if (!(dis < R(0))) {
+                const R p = O::div(O::add(delta, O::sqrt(dis)), sumQ);
+                const R tp0 = O::sub(t0, p), tp1 = O::sub(t1, p);
+                const R T = O::add(O::abs(tp0), O::abs(tp1));
+                const R M = O::mul(O::mul(Q.Q00 > Q.Q11 ? Q.Q00 : Q.Q11, T), SignShort<R>::margin());
+                const R e0 = O::add(O::mul(Q.Q00, tp0), O::mul(Q.Q01, tp1)), e1 = O::add(O::mul(Q.Q01, tp0), O::mul(Q.Q11, tp1));
+                dec = T >= SignShort<R>::t_min() && T <= SignShort<R>::t_max() && O::abs(e0) > M && O::abs(e1) > M;
+            }
+        }
+        decided += dec ? 1u : 0u;
+        if (fb_full != fb_short || !B::same(pf, ps)) bad++;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (decided) atomicAdd(out + 1, decided);
+    if (flagged) atomicAdd(out + 2, flagged);
 }
 
 // DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
@@ -800,7 +889,8 @@ struct ptp_mesh {
     u32 *ring8 = nullptr;
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
-    unsigned char *safe8 = nullptr; // causal-safe triangle flags, built at the first batched call (k_safe_build)
+    unsigned char *safe8 = nullptr; // [2V] causal-safe / short-sign-test triangle flags, built at the first batched call (k_safe_build)
+    int safe_sign = -1;             // whether safe8[V..2V) was built with the "sign_short" option on
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
     bool geo_failed = false; // the table did not fit: do not try again
     bool two_failed = false; // the two-launch single solve did not get both kernels resident once: use one launch from now on
@@ -1097,11 +1187,14 @@ template <class R> int ensure_geo(ptp_mesh *m, cudaStream_t stream, bool *ok)
 
 template <class R> int ensure_safe(ptp_mesh *m, cudaStream_t stream)
 {
-    if (m->safe8) return PTP_OK;
+    const int with_sign = (PTP_SIGN_SHORT && opt("sign_short") != 0) ? 1 : 0;
+    if (m->safe8 && m->safe_sign == with_sign) return PTP_OK;
     int rc;
-    if ((rc = dev_alloc(m, (void **)&m->safe8, m->V, nullptr))) return rc;
-    k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8);
+    if (!m->safe8 && (rc = dev_alloc(m, (void **)&m->safe8, 2 * m->V, nullptr))) return rc;
+    k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8,
+                                                                     (u32)with_sign);
     CK(cudaGetLastError());
+    m->safe_sign = with_sign;
     return PTP_OK;
 }
 
@@ -1799,9 +1892,9 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     CK(cudaMemsetAsync(queue, 0, 128, stream));
     CK(cudaMemsetAsync(m->bt_ctrl, 0, 8 * C_COUNT * (u64)m->bt_slots, stream));
     CK(cudaEventRecord(m->ev[0], stream));
-    // causal skip ("causal" option): needs the per-mesh safe flags and 30-bit ranks; not combined with the geometry table
+    // causal skip ("causal" option): needs the per-mesh safe flags and 29-bit ranks; not combined with the geometry table
     // (whose records are indexed by the un-rotated ring slots)
-    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (1ull << 30);
+    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (u64)RANK_MASK;
     if (causal && (rc = ensure_safe<R>(m, stream))) return rc;
     MeshView<R> mv = mesh_view<R>(m);
     if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
@@ -2010,7 +2103,8 @@ template <class R> int update_positions(ptp_mesh *m, const R *GT)
         k_pad_gt<R><<<(unsigned)((m->V * 4 + 255) / 256), 256, 0, m->stream>>>((const R *)d_gt, (R *)m->GT4, (u32)m->V);
         CK(cudaGetLastError());
         if (m->safe8) {
-            k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, m->stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8);
+            k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, m->stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8,
+                                                                                 (u32)m->safe_sign);
             CK(cudaGetLastError());
         }
         if (m->geo) { // the geometry table depends on the positions
@@ -2361,6 +2455,25 @@ int ptp_debug_inv_gram_check(uint64_t n, uint64_t seed, int real_size, uint64_t 
     if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
     if (mismatches) *mismatches = h[0];
     if (shared_path) *shared_path = h[1];
+    return PTP_OK;
+}
+
+// verification helper (not part of the reference interface): see k_dbg_sign_short
+int ptp_debug_sign_short_check(uint64_t n, uint64_t seed, int real_size, uint64_t *disagreements, uint64_t *decided, uint64_t *flagged)
+{
+    ull *out = nullptr;
+    if (real_size != 4 && real_size != 8) return fail(PTP_ERR_INVALID, "real_size must be 4 or 8");
+    if (cudaMalloc(&out, 24) != cudaSuccess) { cudaGetLastError(); return fail(PTP_ERR_NO_DEVICE, "no CUDA device"); }
+    cudaMemset(out, 0, 24);
+    if (real_size == 4) k_dbg_sign_short<float><<<1184, 256>>>((ull)n, (ull)seed, out);
+    else k_dbg_sign_short<double><<<1184, 256>>>((ull)n, (ull)seed, out);
+    ull h[3] = {0, 0, 0};
+    const cudaError_t e = cudaMemcpy(h, out, 24, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
+    if (disagreements) *disagreements = h[0];
+    if (decided) *decided = h[1];
+    if (flagged) *flagged = h[2];
     return PTP_OK;
 }
 

@@ -212,6 +212,16 @@ double ptp_debug_barrier_ns(int ctas, int block, int n);
 int ptp_debug_inv_gram_check(uint64_t n, uint64_t seed, int real_size, uint64_t *mismatches, uint64_t *shared_path,
                              double *samples160);
 
+/* Verification helper, not part of the reference interface: the batched sweep decides the acceptance condition of
+ * update_step (src/geodesics_ptp.cpp:239-253: c0 < 0 and c1 < 0 after 43 rounded operations) from its two-term form
+ * e = Q (t - p) wherever |e| exceeds a proven bound on the difference of the two evaluations (csrc/ptp_device.cuh,
+ * tri_front). This runs both on `n` generated cases — random triangles within and at the edge of the admitted shapes,
+ * distances random or chosen so that e nearly cancels — and counts the cases in which the short form decided and the
+ * reference chain disagrees (*disagreements, expected 0), the cases it decided (*decided) and the cases generated on
+ * admitted triangles (*flagged). real_size = 4 | 8. */
+int ptp_debug_sign_short_check(uint64_t n, uint64_t seed, int real_size, uint64_t *disagreements, uint64_t *decided,
+                               uint64_t *flagged);
+
 #ifdef __cplusplus
 }
 #endif

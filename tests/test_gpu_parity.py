@@ -350,3 +350,20 @@ def test_inv_gram_shared_reciprocal_is_ieee_division(real_size):
     _lib.check(L.ptp_debug_inv_gram_check(n, 20261017 + real_size, real_size, C.byref(bad), C.byref(fast), None))
     assert bad.value == 0
     assert fast.value > n // 8  # the well-shaped geometric cases at moderate scales take the shared path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real_size", [4, 8])
+def test_short_sign_test_agrees_with_reference_chain(real_size):
+    """update_step keeps the planar value iff c0 < 0 and c1 < 0 (src/geodesics_ptp.cpp:239-253). The batched sweep reads the
+    signs off the two-term form e = Q (t - p) when |e| is above a proven bound; wherever it decides, the decision (and the
+    returned value) must be the reference chain's — on random triangles up to the edge of the admitted shapes and on
+    adversarial distances that make e nearly cancel."""
+    import ctypes as C
+    from gproshan_b200 import _lib
+    L = _lib.lib()
+    bad, dec, flg = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    n = 300_000_000
+    _lib.check(L.ptp_debug_sign_short_check(n, 4242 + real_size, real_size, C.byref(bad), C.byref(dec), C.byref(flg)))
+    assert bad.value == 0
+    assert flg.value > n // 4 and dec.value > flg.value // 4  # the test must exercise the short form

@@ -23,6 +23,7 @@ VARIANTS = [
     ("geometry-table", {"PTP_GEO": "1", "PTP_GEO_SINGLE": "1"}, None),
     ("no-elastic", {"PTP_ELASTIC": "0"}, None),
     ("no-causal-skip", {"PTP_CAUSAL": "0"}, None),
+    ("no-short-sign-test", {"PTP_SIGN_SHORT": "0"}, None),
     ("batched-teams-of-4", {"PTP_TEAM": "4"}, None),
     ("batched-teams-of-37-no-causal", {"PTP_TEAM": "37", "PTP_CAUSAL": "0"}, None),
     ("newest-buffer-off-explicit", {"PTP_NEWEST": "0"}, None),

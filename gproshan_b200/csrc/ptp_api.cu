@@ -555,6 +555,20 @@ __global__ void k_dbg_sign_short(ull n, ull seed, ull *out)
     if (flagged) atomicAdd(out + 2, flagged);
 }
 
+// DEBUG / verification: Ops<float>::sqrt_n against __fsqrt_rn over EVERY float in [2^-96, 2^96] (ptp_debug_sqrt_check)
+__global__ void k_dbg_sqrt(ull *out)
+{
+    ull bad = 0, n = 0;
+    const u32 lo = (127u - 96u) << 23, hi = (127u + 96u) << 23; // bit patterns of 2^-96 and 2^96
+    for (ull b = (ull)lo + blockIdx.x * (ull)blockDim.x + threadIdx.x; b <= (ull)hi; b += (ull)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((u32)b);
+        bad += __float_as_uint(Ops<float>::sqrt_n(x)) != __float_as_uint(__fsqrt_rn(x)) ? 1u : 0u;
+        n++;
+    }
+    if (bad) atomicAdd(out, bad);
+    atomicAdd(out + 1, n);
+}
+
 // DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
 // mode 0: barriers only. mode 1: every iteration each CTA writes a word, barrier, every thread reads the word its
 // neighbour CTA wrote (plain load: the acquire barrier flushed L1) and the value feeds the next iteration — the
@@ -1894,7 +1908,7 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     CK(cudaEventRecord(m->ev[0], stream));
     // causal skip ("causal" option): needs the per-mesh safe flags and 29-bit ranks; not combined with the geometry table
     // (whose records are indexed by the un-rotated ring slots)
-    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (u64)RANK_MASK;
+    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (PTP_ROLLED == 3 ? (1ull << 28) : (u64)RANK_MASK);
     if (causal && (rc = ensure_safe<R>(m, stream))) return rc;
     MeshView<R> mv = mesh_view<R>(m);
     if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
@@ -2474,6 +2488,22 @@ int ptp_debug_sign_short_check(uint64_t n, uint64_t seed, int real_size, uint64_
     if (disagreements) *disagreements = h[0];
     if (decided) *decided = h[1];
     if (flagged) *flagged = h[2];
+    return PTP_OK;
+}
+
+// verification helper (not part of the reference interface): see k_dbg_sqrt
+int ptp_debug_sqrt_check(uint64_t *mismatches, uint64_t *tested)
+{
+    ull *out = nullptr;
+    if (cudaMalloc(&out, 16) != cudaSuccess) { cudaGetLastError(); return fail(PTP_ERR_NO_DEVICE, "no CUDA device"); }
+    cudaMemset(out, 0, 16);
+    k_dbg_sqrt<<<1184, 256>>>(out);
+    ull h[2] = {0, 0};
+    const cudaError_t e = cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
+    if (mismatches) *mismatches = h[0];
+    if (tested) *tested = h[1];
     return PTP_OK;
 }
 

@@ -222,6 +222,11 @@ int ptp_debug_inv_gram_check(uint64_t n, uint64_t seed, int real_size, uint64_t 
 int ptp_debug_sign_short_check(uint64_t n, uint64_t seed, int real_size, uint64_t *disagreements, uint64_t *decided,
                                uint64_t *flagged);
 
+/* Verification helper, not part of the reference interface: on triangles whose per-mesh flag bounds the squared edge
+ * lengths, the float square root of the Dijkstra fallback (src/geodesics_ptp.cpp:254-259) runs the IEEE sequence without
+ * its range test; this compares the two forms over EVERY float of [2^-96, 2^96] (*tested of them; *mismatches expected 0). */
+int ptp_debug_sqrt_check(uint64_t *mismatches, uint64_t *tested);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,3 +367,14 @@ def test_short_sign_test_agrees_with_reference_chain(real_size):
     _lib.check(L.ptp_debug_sign_short_check(n, 4242 + real_size, real_size, C.byref(bad), C.byref(dec), C.byref(flg)))
     assert bad.value == 0
     assert flg.value > n // 4 and dec.value > flg.value // 4  # the test must exercise the short form
+
+
+@pytest.mark.gpu
+def test_range_free_sqrt_is_ieee_sqrt():
+    """every float in [2^-96, 2^96]: the square root without the range test (the PTP_FLAG_RANGE build variant uses it where a
+    triangle's flag bounds the argument; in the default build sqrt_n IS __fsqrt_rn) equals __fsqrt_rn bit for bit"""
+    import ctypes as C
+    from gproshan_b200 import _lib
+    bad, n = C.c_uint64(0), C.c_uint64(0)
+    _lib.check(_lib.lib().ptp_debug_sqrt_check(C.byref(bad), C.byref(n)))
+    assert bad.value == 0 and n.value == 192 * (1 << 23) + 1

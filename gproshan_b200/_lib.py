@@ -40,7 +40,7 @@ SYMBOLS = [
     "ptp_toplesets", "ptp_solve_f32", "ptp_solve_f64", "ptp_geodesics_f32", "ptp_geodesics_f64",
     "ptp_geodesics_error_iter_f32", "ptp_geodesics_error_iter_f64",
     "ptp_solve_batched_f32", "ptp_solve_batched_f64", "ptp_solve_batched_multi_f32", "ptp_solve_batched_multi_f64",
-    "ptp_farthest_point_sampling_f32", "ptp_farthest_point_sampling_f64", "ptp_debug_barrier_ns", "ptp_debug_inv_gram_check", "ptp_debug_sign_short_check", "ptp_debug_sqrt_check",
+    "ptp_farthest_point_sampling_f32", "ptp_farthest_point_sampling_f64", "ptp_debug_barrier_ns", "ptp_debug_inv_gram_check", "ptp_debug_sign_short_check", "ptp_debug_sqrt_check", "ptp_debug_two_sided_check",
 ]
 
 _LIB = None
@@ -91,6 +91,7 @@ def lib():
     L.ptp_debug_barrier_ns.restype = C.c_double
     L.ptp_debug_sign_short_check.argtypes = [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p, u64p]
     L.ptp_debug_sqrt_check.argtypes = [u64p, u64p]
+    L.ptp_debug_two_sided_check.argtypes = [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p, u64p]
     L.ptp_debug_inv_gram_check.argtypes = [C.c_uint64, C.c_uint64, C.c_int, u64p, u64p, C.POINTER(C.c_double)]
     L.ptp_mesh_last_kernel.argtypes = [vp]
     L.ptp_mesh_last_kernel.restype = C.c_char_p

@@ -65,6 +65,7 @@ Option g_options[] = {
     {"elastic", 1, "one-CTA-per-solve batched kernel: idle CTAs execute ticketed chunks of running solves"},
     {"causal", 1, "batched solves skip triangles that provably cannot lower a vertex (both neighbours above it; bit-exact)"},
     {"sign_short", 1, "batched solves (with causal) decide update_step's acceptance condition from its two-term form where provably equal (bit-exact)"},
+    {"two_sided", 1, "batched solves (with causal) also skip triangles with one corner above the vertex when the other provably cannot reach it (bit-exact)"},
     {"team", 0, "batched solves: CTAs per solve (0 = 1 when the batch fills the chip, num_sms / batch otherwise; 1 = always one CTA per solve)"},
     {"newest", 0, "return the Jacobi buffer WRITTEN by the last iteration (what the reference's CUDA code copies back, "
                   "src/cuda/geodesics_ptp.cu:60-66) instead of the one it read (the reference's CPU code, src/geodesics_ptp.cpp:193-198)"},
@@ -276,7 +277,7 @@ __global__ void k_geo_build(const typename Ops<R>::vec4 *__restrict__ GT4, const
 // "sign_short" option is off).
 template <class R>
 __global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, const u32 *__restrict__ ring8, u32 V, unsigned char *__restrict__ safe8,
-                             u32 with_sign)
+                             u32 with_sign, u32 with_two)
 {
     typedef Ops<R> O;
     const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +285,7 @@ __global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, cons
     const u32 *row = ring8 + (size_t)v * GL;
     u32 e[GL];
     for (u32 k = 0; k < GL; k++) e[k] = row[k];
-    u32 len = 0, bits = 0, sbits = 0;
+    u32 len = 0, bits = 0, sbits = 0, tbits = 0;
     bool open = false;
     if (e[0] != OVF && e[0] != NIL) {
         open = (e[0] & OPEN_BIT) != 0;
@@ -308,9 +309,11 @@ __global__ void k_safe_build(const typename Ops<R>::vec4 *__restrict__ GT4, cons
             const R det = O::sub(O::mul(q[k], q[k1]), O::mul(q01, q01)); // as update_step computes it
             if (sign_short_ok<R>(q[k], q[k1], det)) sbits |= 1u << k;
         }
+        if (with_two && two_sided_ok<R>(X[k], X[k1], q[k], q[k1])) tbits |= 1u << k; // (safe8[2V + v]: two-sided causal skip)
     }
     safe8[v] = (unsigned char)bits;
     safe8[(size_t)V + v] = (unsigned char)sbits;
+    safe8[2 * (size_t)V + v] = (unsigned char)tbits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,6 +570,67 @@ __global__ void k_dbg_sqrt(ull *out)
     }
     if (bad) atomicAdd(out, bad);
     atomicAdd(out + 1, n);
+}
+
+// DEBUG / verification: the two-sided causal skip (two_sided_ok + two_sided_skip) against update_step
+// (ptp_debug_two_sided_check). Triangles of random shape and scale, and around each (cur, lo, hi) random or ADVERSARIAL:
+// hi - cur at the edge of what (G) admits, thr - lo within rounding of the edge length (the boundary of (E)), hi = thr
+// exactly, cur = 0, lo = 0. Whenever the rule fires the reference chain is evaluated (sign_short off):
+// out[0] = cases with p < cur (expected 0), out[1] = cases in which the rule fired, out[2] = cases on admitted triangles.
+template <class R>
+__global__ void k_dbg_two_sided(ull n, ull seed, ull *out)
+{
+    typedef Ops<R> O;
+    typedef DbgBits<R> B;
+    ull bad = 0, fired = 0, flagged = 0;
+    for (ull i = blockIdx.x * (ull)blockDim.x + threadIdx.x; i < n; i += (ull)gridDim.x * blockDim.x) {
+        ull h = dbg_mix(seed ^ (i * 0xD1342543DE82EF95ull));
+        auto unif = [&]() -> double { h = dbg_mix(h); return (double)(long long)(h >> 11) * (1.0 / 9007199254740992.0); };
+        const u32 kind = (u32)(h & 15u);
+        const int e = (int)((h >> 8) % 25u) - 12;
+        const double len0 = 1.0 + unif(), len1 = len0 * (kind & 1 ? 1.0 + 1.9 * unif() : 1.0 / (1.0 + 1.9 * unif()));
+        const double ang = (15.0 + 78.0 * unif()) * 0.017453292519943295; // up to 93 degrees: the flag must reject the obtuse ones
+        double f0[3] = {unif() - 0.5, unif() - 0.5, unif() - 0.5}, f1[3] = {unif() - 0.5, unif() - 0.5, unif() - 0.5};
+        const double n0 = sqrt(f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2]) + 1e-300;
+        for (int k = 0; k < 3; k++) f0[k] /= n0;
+        const double dt = f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2];
+        for (int k = 0; k < 3; k++) f1[k] -= dt * f0[k];
+        const double n1 = sqrt(f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2]) + 1e-300;
+        for (int k = 0; k < 3; k++) f1[k] /= n1;
+        const double sc = (double)B::scale(e);
+        P3<R> X0, X1;
+        X0.x = (R)(len0 * f0[0] * sc); X0.y = (R)(len0 * f0[1] * sc); X0.z = (R)(len0 * f0[2] * sc);
+        X1.x = (R)(len1 * (cos(ang) * f0[0] + sin(ang) * f1[0]) * sc);
+        X1.y = (R)(len1 * (cos(ang) * f0[1] + sin(ang) * f1[1]) * sc);
+        X1.z = (R)(len1 * (cos(ang) * f0[2] + sin(ang) * f1[2]) * sc);
+        const R q00 = dot3(X0, X0), q11 = dot3(X1, X1);
+        if (!two_sided_ok<R>(X0, X1, q00, q11)) continue;
+        flagged++;
+        const bool lo_is_0 = ((h >> 20) & 1) != 0;                      // which corner is the upstream one
+        const double x_lo = sqrt((double)(lo_is_0 ? q00 : q11));
+        // lo: far from / near / at the sources; cur above it by a fraction of the edge; hi above cur
+        double lo = sc * (kind < 12 ? 4.0 + 800.0 * unif() : (kind < 14 ? 2.0 * unif() : 0.0));
+        double cur = lo + x_lo * 1.3 * unif();
+        if (kind == 15) { cur = 0.0; lo = 0.0; }
+        const double gap = cur - lo;
+        double hi = cur + sc * len0 * 1.5 * unif();
+        const u32 adv = (u32)((h >> 24) & 7u);
+        if (adv == 1) hi = cur + gap * ldexp(1.0, -9) * (1.0 + ldexp(unif() - 0.5, -18));      // (G) at its edge
+        if (adv == 2) hi = cur * (1.0 + ldexp(1.0, -14)) * (1.0 + ldexp(unif() - 0.5, -20));   // hi ~ thr
+        if (adv == 3) cur = (lo + x_lo) * (1.0 - ldexp(1.0, -14)) * (1.0 + ldexp(unif() - 0.5, -16)), hi = cur + sc * len0 * unif(); // (E) at its edge
+        if (adv == 4) hi = cur + ldexp(1.0, -39) * (1.0 + unif());                             // g ~ g_min
+        const R rcur = (R)cur, rlo = (R)lo, rhi = (R)hi;
+        const R thr = O::mul(rcur, Causal<R>::up());
+        const R t0 = lo_is_0 ? rlo : rhi, t1 = lo_is_0 ? rhi : rlo;
+        // (the arguments exactly as the ring walk forms them: corner 0 = current neighbour, corner 1 = next)
+        if (!two_sided_skip<R>(rcur, thr, t1 < t0 ? t1 : t0, t1 < t0 ? t0 : t1, t1 < t0 ? q11 : q00)) continue;
+        fired++;
+        const R p = update_tri<R>(X0, X1, q00, q11, t0, t1, false);
+        if (p < rcur) bad++;
+    }
+    if (bad) atomicAdd(out, bad);
+    if (fired) atomicAdd(out + 1, fired);
+    if (flagged) atomicAdd(out + 2, flagged);
 }
 
 // DEBUG / measurement: n grid barriers and nothing else (ptp_debug_barrier_ns)
@@ -903,8 +967,8 @@ struct ptp_mesh {
     u32 *ring8 = nullptr;
     u32 *ovf = nullptr;
     u64 ovf_total = 0;
-    unsigned char *safe8 = nullptr; // [2V] causal-safe / short-sign-test triangle flags, built at the first batched call (k_safe_build)
-    int safe_sign = -1;             // whether safe8[V..2V) was built with the "sign_short" option on
+    unsigned char *safe8 = nullptr; // [3V] causal-safe / short-sign-test / two-sided-skip triangle flags, built at the first batched call (k_safe_build)
+    int safe_sign = -1;             // options safe8[V..3V) was built with: bit 0 "sign_short", bit 1 "two_sided"
     void *geo = nullptr; // geometry table, built at the first batched call (k_geo_build)
     bool geo_failed = false; // the table did not fit: do not try again
     bool two_failed = false; // the two-launch single solve did not get both kernels resident once: use one launch from now on
@@ -1201,12 +1265,12 @@ template <class R> int ensure_geo(ptp_mesh *m, cudaStream_t stream, bool *ok)
 
 template <class R> int ensure_safe(ptp_mesh *m, cudaStream_t stream)
 {
-    const int with_sign = (PTP_SIGN_SHORT && opt("sign_short") != 0) ? 1 : 0;
+    const int with_sign = ((PTP_SIGN_SHORT && opt("sign_short") != 0) ? 1 : 0) | ((PTP_SIGN_SHORT && PTP_TWO_SIDED && opt("two_sided") != 0) ? 2 : 0);
     if (m->safe8 && m->safe_sign == with_sign) return PTP_OK;
     int rc;
-    if (!m->safe8 && (rc = dev_alloc(m, (void **)&m->safe8, 2 * m->V, nullptr))) return rc;
+    if (!m->safe8 && (rc = dev_alloc(m, (void **)&m->safe8, 3 * m->V, nullptr))) return rc;
     k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8,
-                                                                     (u32)with_sign);
+                                                                     (u32)(with_sign & 1), (u32)(with_sign >> 1));
     CK(cudaGetLastError());
     m->safe_sign = with_sign;
     return PTP_OK;
@@ -1906,9 +1970,9 @@ int batched_impl(ptp_mesh *m, const u32 *sources, const u64 *offsets, u32 B, u64
     CK(cudaMemsetAsync(queue, 0, 128, stream));
     CK(cudaMemsetAsync(m->bt_ctrl, 0, 8 * C_COUNT * (u64)m->bt_slots, stream));
     CK(cudaEventRecord(m->ev[0], stream));
-    // causal skip ("causal" option): needs the per-mesh safe flags and 29-bit ranks; not combined with the geometry table
+    // causal skip ("causal" option): needs the per-mesh safe flags and 28-bit ranks (three flag bits per ring entry, 32-bit record offsets); not combined with the geometry table
     // (whose records are indexed by the un-rotated ring slots)
-    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (PTP_ROLLED == 3 ? (1ull << 28) : (u64)RANK_MASK);
+    const bool causal = opt("causal") != 0 && !use_geo && m->V + m->bt_scap + 2 < (1ull << 28);
     if (causal && (rc = ensure_safe<R>(m, stream))) return rc;
     MeshView<R> mv = mesh_view<R>(m);
     if (!use_geo) mv.geo = nullptr; // (the single-solve path may have built the table; the batched kernel uses it on request only)
@@ -2118,7 +2182,7 @@ template <class R> int update_positions(ptp_mesh *m, const R *GT)
         CK(cudaGetLastError());
         if (m->safe8) {
             k_safe_build<R><<<(unsigned)((m->V + 127) / 128), 128, 0, m->stream>>>((const typename Ops<R>::vec4 *)m->GT4, m->ring8, (u32)m->V, m->safe8,
-                                                                                 (u32)m->safe_sign);
+                                                                                 (u32)(m->safe_sign & 1), (u32)(m->safe_sign >> 1));
             CK(cudaGetLastError());
         }
         if (m->geo) { // the geometry table depends on the positions
@@ -2504,6 +2568,25 @@ int ptp_debug_sqrt_check(uint64_t *mismatches, uint64_t *tested)
     if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
     if (mismatches) *mismatches = h[0];
     if (tested) *tested = h[1];
+    return PTP_OK;
+}
+
+// verification helper (not part of the reference interface): see k_dbg_two_sided
+int ptp_debug_two_sided_check(uint64_t n, uint64_t seed, int real_size, uint64_t *violations, uint64_t *fired, uint64_t *flagged)
+{
+    ull *out = nullptr;
+    if (real_size != 4 && real_size != 8) return fail(PTP_ERR_INVALID, "real_size must be 4 or 8");
+    if (cudaMalloc(&out, 24) != cudaSuccess) { cudaGetLastError(); return fail(PTP_ERR_NO_DEVICE, "no CUDA device"); }
+    cudaMemset(out, 0, 24);
+    if (real_size == 4) k_dbg_two_sided<float><<<1184, 256>>>((ull)n, (ull)seed, out);
+    else k_dbg_two_sided<double><<<1184, 256>>>((ull)n, (ull)seed, out);
+    ull h[3] = {0, 0, 0};
+    const cudaError_t e = cudaMemcpy(h, out, 24, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(PTP_ERR_CUDA, cudaGetErrorString(e));
+    if (violations) *violations = h[0];
+    if (fired) *fired = h[1];
+    if (flagged) *flagged = h[2];
     return PTP_OK;
 }
 

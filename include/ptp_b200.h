@@ -227,6 +227,14 @@ int ptp_debug_sign_short_check(uint64_t n, uint64_t seed, int real_size, uint64_
  * its range test; this compares the two forms over EVERY float of [2^-96, 2^96] (*tested of them; *mismatches expected 0). */
 int ptp_debug_sqrt_check(uint64_t *mismatches, uint64_t *tested);
 
+/* Verification helper, not part of the reference interface: the batched sweep skips a triangle with ONE corner above the
+ * vertex when update_step (src/geodesics_ptp.cpp:201-262) provably cannot return a value below the vertex's (two-sided
+ * causal skip, csrc/ptp_device.cuh: two_sided_ok / two_sided_skip). This evaluates the reference chain on `n` generated
+ * cases — random triangles, distances random or at the edges of the rule — and counts the cases in which the rule fired and
+ * update_step returned less than the vertex's value (*violations, expected 0), the cases in which it fired (*fired) and
+ * the cases generated on admitted triangles (*flagged). real_size = 4 | 8. */
+int ptp_debug_two_sided_check(uint64_t n, uint64_t seed, int real_size, uint64_t *violations, uint64_t *fired, uint64_t *flagged);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ void analyze_f32(uint32_t n_v, const float *GT, const uint32_t *VT, const uint32
     int32_t *seen = calloc(n_v, 4);   /* how many times the vertex has been in the window */
     for (uint32_t v = 0; v < n_v; v++) { d[0][v] = d[1][v] = INFINITY; chgs[0][v] = chgs[1][v] = -10; }
     for (uint32_t i = 0; i < n_sources; i++) d[0][sources[i]] = d[1][sources[i]] = 0;
-    memset(out, 0, 8 * 8);
+    memset(out, 0, 8 * 10);
     uint32_t i = 1, j = 2, dd = 0, iter = 0, max_iter = n_limits << 1;
     int32_t k = 0;
     while (n_limits >= 3 && i < j && iter++ < max_iter) {
@@ -60,6 +60,17 @@ void analyze_f32(uint32_t n_v, const float *GT, const uint32_t *VT, const uint32
                     const int changed = seen[v] < 2 || chg[a] == k - 1 || chg[b] == k - 1;
                     const float lo = od[a] < od[b] ? od[a] : od[b];
                     const int causal = !(lo > od[v] * (1.0f + 0x1p-14f) && lo >= 0x1p-60f);
+                    {   /* potential of a two-sided causal bound: p >= min(max(t_a, t_b), min_i (t_i + |X_i|)) */
+                        float Xa[3], Xb[3];
+                        for (int c = 0; c < 3; c++) { Xa[c] = GT[3 * (size_t)a + c] - GT[3 * (size_t)v + c]; Xb[c] = GT[3 * (size_t)b + c] - GT[3 * (size_t)v + c]; }
+                        const float ea = od[a] + norm3_f32(Xa), eb = od[b] + norm3_f32(Xb);
+                        const float hi = od[a] > od[b] ? od[a] : od[b];
+                        const float e = ea < eb ? ea : eb;
+                        const float bound = hi < e ? hi : e;
+                        static uint64_t dummy; (void)dummy;
+                        if (causal && bound > od[v] * (1.0f + 0x1p-14f)) out[8]++;
+                        if (causal && bound > od[v] * (1.0f + 0x1p-14f) && !(p >= od[v])) out[9]++; /* bound violated: p would have mattered */
+                    }
                     out[1]++;
                     out[2] += changed;
                     out[6] += causal;

@@ -23,7 +23,7 @@ orc = ol.Oracle()
 src = np.array([12345 % mesh.n_vertices], dtype=np.uint32)
 tl, srt, lim = orc.compute_toplesets(mesh, src)
 u32p, fp = C.POINTER(C.c_uint32), C.POINTER(C.c_float)
-out = (C.c_uint64 * 8)()
+out = (C.c_uint64 * 10)()
 p = lambda a, t=C.c_uint32: a.ctypes.data_as(C.POINTER(t))
 GT = np.ascontiguousarray(mesh.GT, dtype=np.float32)
 L.analyze_f32(mesh.n_vertices, p(GT, C.c_float), p(mesh.VT), p(mesh.OT), p(mesh.EVT), p(src), 1, p(lim), lim.size, p(srt), out)
@@ -32,3 +32,4 @@ print("V", mesh.n_vertices, "vertex-updates", o[3], "relaxations", o[0], "(%.1f 
 print("triangles", o[1], "with a changed corner", o[2], "(%.1f %%)" % (100 * o[2] / o[1]), "| causal-pass", o[6], "(%.1f %%)" % (100 * o[6] / o[1]),
       "| both", o[5], "(%.1f %%)" % (100 * o[5] / o[1]))
 print("restricted-minimum mismatches", o[4], "skip mismatches", o[7])
+print("two-sided bound: additionally skippable among causal-pass", o[8], "(%.1f %% of all triangles)" % (100 * o[8] / o[1]), "violations", o[9])

@@ -69,7 +69,7 @@ def test_reference_gpu_leg_degrades_without_a_gpu():
 def test_option_table_is_documented_and_settable():
     """ptp_set_option / ptp_get_option / ptp_option_name / ptp_option_doc: one table, no hidden getenv switches."""
     opts = api.options()
-    for name in ("fused", "stage", "cluster", "geo", "elastic", "causal", "sign_short", "team", "newest", "gather_chunks", "profile_range"):
+    for name in ("fused", "stage", "cluster", "geo", "elastic", "causal", "sign_short", "two_sided", "team", "newest", "gather_chunks", "profile_range"):
         assert name in opts and len(opts[name][1]) > 10, name
     old = api.get_option("gather_chunks")
     api.set_option("gather_chunks", 5)

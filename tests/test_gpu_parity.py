@@ -378,3 +378,17 @@ def test_range_free_sqrt_is_ieee_sqrt():
     bad, n = C.c_uint64(0), C.c_uint64(0)
     _lib.check(_lib.lib().ptp_debug_sqrt_check(C.byref(bad), C.byref(n)))
     assert bad.value == 0 and n.value == 192 * (1 << 23) + 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real_size", [4, 8])
+def test_two_sided_skip_never_hides_an_improvement(real_size):
+    """whenever the two-sided causal skip fires, update_step (reference chain) returns a value that is not below the
+    vertex's — on random triangles and on inputs placed at the edges of the rule"""
+    import ctypes as C
+    from gproshan_b200 import _lib
+    bad, fired, flg = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    n = 300_000_000
+    _lib.check(_lib.lib().ptp_debug_two_sided_check(n, 777 + real_size, real_size, C.byref(bad), C.byref(fired), C.byref(flg)))
+    assert bad.value == 0
+    assert flg.value > n // 8 and fired.value > flg.value // 8  # the test must exercise the rule

@@ -24,6 +24,7 @@ VARIANTS = [
     ("no-elastic", {"PTP_ELASTIC": "0"}, None),
     ("no-causal-skip", {"PTP_CAUSAL": "0"}, None),
     ("no-short-sign-test", {"PTP_SIGN_SHORT": "0"}, None),
+    ("no-two-sided-skip", {"PTP_TWO_SIDED": "0"}, None),
     ("batched-teams-of-4", {"PTP_TEAM": "4"}, None),
     ("batched-teams-of-37-no-causal", {"PTP_TEAM": "37", "PTP_CAUSAL": "0"}, None),
     ("newest-buffer-off-explicit", {"PTP_NEWEST": "0"}, None),

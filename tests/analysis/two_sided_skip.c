@@ -21,6 +21,8 @@ static inline uint32_t he_prev(uint32_t he) { return 3 * (he / 3) + (he + 2) % 3
 
 /* out: 0 relaxations, 1 triangle slots, 2 lane-level evaluated (old rule), 3 lane-level evaluated (old + new rule),
  *      4 warp-slots total, 5 warp-slots evaluated (old), 6 warp-slots evaluated (old + new), 7 violations (new rule fired, p < cur) */
+static uint64_t extra[4];
+void analyze2_extra(uint64_t *o) { for (int i = 0; i < 4; i++) o[i] = extra[i]; }
 void analyze2_f32(uint32_t n_v, const float *GT, const uint32_t *VT, const uint32_t *OT, const uint32_t *EVT, const uint32_t *sources,
                   uint32_t n_sources, const uint32_t *limits, uint32_t n_limits, const uint32_t *sorted, const uint32_t *inv, uint64_t *out)
 {
@@ -79,6 +81,7 @@ void analyze2_f32(uint32_t n_v, const float *GT, const uint32_t *VT, const uint3
                         new_skip = (hi - cur) >= 0x1p-9f * gap && (hi - cur) >= 0x1p-39f && hi <= 0x1p23f && edge_ok;
                     }
                     if (new_skip && p < cur) out[7]++;
+                    if (!old_skip && !new_skip) { extra[0]++; if (p < cur) extra[1]++; if (hi < thr) extra[2]++; }
                     out[1]++;
                     out[2] += !old_skip;
                     out[3] += !old_skip && !new_skip;

@@ -35,3 +35,6 @@ print("V", mesh.n_vertices, "relaxations", o[0], "triangle slots", o[1])
 print("lane level: evaluated with the causal skip %.1f %%, with the two-sided skip as well %.1f %%" % (100 * o[2] / o[1], 100 * o[3] / o[1]))
 print("warp level: evaluated with the causal skip %.1f %%, with the two-sided skip as well %.1f %%" % (100 * o[5] / o[4], 100 * o[6] / o[4]))
 print("violations (rule fired, p < cur):", o[7])
+ex = (C.c_uint64 * 4)()
+L.analyze2_extra(ex)
+print("of the %d triangles still evaluated: %.1f %% return p < cur, %.1f %% have both corners below thr" % (ex[0], 100 * ex[1] / max(ex[0], 1), 100 * ex[2] / max(ex[0], 1)))
